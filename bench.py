@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- la3dm_b200 headline benchmark: BGKOctoMap::insert_pointcloud on synthetic 64 k-point scans
+(50 m extent, 0.1 m resolution, config/methods/bgkoctomap.yaml parameters), voxel-updates per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one insert_pointcloud() of one scan of a seeded synthetic sequence (la3dm_b200/synthetic.py) into a map
+that starts empty before the warm-up scans; scan i of the run is sequence[i].  Units:
+  voxel-visit  = one leaf of one test block processed by the scan,
+  voxel-update = a visit for which Occupancy::update fired (kbar guard passed)  <- the metric's unit.
+Three measurements on our arm:
+  value   device-resident: the scans already sit in HBM, la3dm_insert_pointcloud_device(), CUDA events on the map's
+          stream around each call, L2 flushed between steps (outside the events);
+  e2e     the reference-facing call la3dm_insert_pointcloud() with pinned HOST clouds: H2D copy of the cloud and D2H
+          read-back of the scan counters happen inside the timed region;
+  cpu_baseline / --impl reference: the reference's own sources (oracle/_ref, "fast" flavour, all host threads).
+N > 1 (torchrun): every rank holds a replica of the map and runs the front-end redundantly, the test blocks of the scan
+are dealt over ranks inside the predict kernel and the updated block rows are exchanged with ONE NCCL all-gather per
+scan; the same scan is split over more GPUs => "scaling": "strong".
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "voxel-updates/sec per scan (64k pts, 0.1 m res)"
+UNIT = "voxel-updates/s"
+BGK = dict(resolution=0.1, block_depth=3, sf2=1.0, ell=0.2, free_thresh=0.3, occupied_thresh=0.7, var_thresh=100.0,
+           prior_A=0.001, prior_B=0.001)          # config/methods/bgkoctomap.yaml
+DS_RES, FREE_RES, MAX_RANGE = 0.1, 0.5, -1.0      # static node passes `resolution` as ds_resolution
+UNITS_FIXTURE = os.path.join(ROOT, "tests", "golden", "synthetic_units_seed1_64k_50m.json")
+
+# algorithmic work of the fused predict/update/prune kernel
+BYTES_PER_VISIT = 17          # (alpha, beta) read 8 B + written 8 B + 1 state byte
+BYTES_PER_MEMBER = 16         # one float4 training entry read once
+BYTES_PER_TEST_BLOCK = 64     # its NeighbourPlan
+FLOP_PER_PAIR = 24
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=65536)
+    ap.add_argument("--extent", type=float, default=50.0)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-sample-scans", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
+    return a
+
+
+def workload_config(a, extra=None):
+    c = {"workload": "BGKOctoMap insert_pointcloud, synthetic %d-pt scans, %g m extent room + 200 spheres, res 0.1, "
+                     "block_depth 3, ell 0.2, free_res 0.5, ds_res 0.1 (bgkoctomap.yaml), seed %d, scan i = "
+                     "sequence[i] into a map empty before warm-up" % (a.points, a.extent, a.seed),
+         "points_per_scan": a.points, "extent_m": a.extent, "seed": a.seed,
+         "l2": "flushed between timed steps (256 MiB write, outside the timed events)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def make_scans(a, n):
+    from la3dm_b200.synthetic import make_sequence
+    return make_sequence(n, a.points, a.extent, a.seed)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own sources (oracle/_ref), all host threads
+# ---------------------------------------------------------------------------------------------------------------------
+def load_unit_fixture(a, n_scans):
+    """Per-scan unit counts of the default workload, produced by the CPU oracle (tests/golden/make_synthetic_units.py).
+    They are properties of the scan sequence, not of an implementation."""
+    if not os.path.exists(UNITS_FIXTURE):
+        return None
+    with open(UNITS_FIXTURE) as f:
+        fx = json.load(f)
+    if fx["points"] != a.points or fx["extent"] != a.extent or fx["seed"] != a.seed or len(fx["scans"]) < n_scans:
+        return None
+    return fx["scans"][:n_scans]
+
+
+def count_units_with_oracle(pts, org):
+    """Fallback for non-default workloads: run the CPU port once (untimed) only to count units per scan."""
+    from oracle.port import PortMap
+    o = PortMap("bgk", dict(BGK))
+    out = []
+    for s in range(len(pts)):
+        o.insert_pointcloud(pts[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
+        st = o.last_stats()
+        out.append({"voxel_visits": st["voxel_visits"], "voxel_updates": st["voxel_updates"],
+                    "kernel_pairs": st["pairs"], "n_train": st["n_train"], "n_test_blocks": st["n_test_blocks"]})
+    return out
+
+
+def ref_available():
+    from oracle import ref
+    return ref.available("bgk", fast=True)
+
+
+def time_reference(pts, org, scan_ids_timed, n_untimed):
+    """Insert scans [0, n_untimed) untimed then the timed ones into a fresh reference map; -> seconds per timed scan."""
+    from oracle.ref import RefMap
+    m = RefMap("bgk", dict(BGK), fast=True)
+    cores = m.max_threads()
+    for s in range(n_untimed):
+        m.insert_pointcloud(pts[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
+    secs = []
+    for s in scan_ids_timed:
+        t0 = time.perf_counter()
+        m.insert_pointcloud(pts[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
+        secs.append(time.perf_counter() - t0)
+    m.close()
+    return secs, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not ref_available():
+        # the reference compiles from its own sources here (oracle/_ref travels to the GPU box); if it is missing the
+        # CPU port stands in (same algorithm, single thread)
+        kind = "port"
+    else:
+        kind = "reference"
+    n = a.warmup + a.steps
+    pts, org = make_scans(a, n)
+    units = load_unit_fixture(a, n) or count_units_with_oracle(pts, org)
+    timed = list(range(a.warmup, n))
+    if kind == "reference":
+        secs, cores = time_reference(pts, org, timed, a.warmup)
+    else:
+        from oracle.port import PortMap
+        o = PortMap("bgk", dict(BGK))
+        cores, secs = 1, []
+        for s in range(n):
+            t0 = time.perf_counter()
+            o.insert_pointcloud(pts[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
+            if s >= a.warmup:
+                secs.append(time.perf_counter() - t0)
+    total = float(sum(secs))
+    upd = sum(units[s]["voxel_updates"] for s in timed)
+    vis = sum(units[s]["voxel_visits"] for s in timed)
+    val = upd / total
+    sample = "scans %d..%d of the sequence, after %d untimed scans into the same map" % (timed[0], timed[-1], a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, {"l2": "n/a (CPU)"}),
+            "voxel_visits_per_s": vis / total,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import la3dm_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (la3dm_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = a.warmup + a.steps
+    pts, org = make_scans(a, n)
+    d_scans = [torch.from_numpy(pts[s]).to(dev) for s in range(n)]
+    h_scans = [torch.from_numpy(pts[s]).pin_memory() for s in range(n)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def new_map():
+        m = la3dm_b200.BGKOctoMap(device=local, **BGK)
+        if world > 1:
+            m.set_shard(rank, world)
+        return m
+
+    def exchange(m, xs):
+        """one all-gather of this scan's updated block rows (NCCL over NVLink), then scatter the peers' rows"""
+        from la3dm_b200 import sharding
+
+        def alloc(nbytes):
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            return t, t.data_ptr()
+
+        def all_gather(out, inp):                  # shard_pack synchronised the map's stream before this runs
+            with torch.cuda.stream(xs):
+                dist.all_gather_into_tensor(out, inp)
+            xs.synchronize()
+
+        return sharding.exchange(m, world, all_gather, alloc)
+
+    def run_pass(host_input):
+        m = new_map()
+        ms_stream = torch.cuda.ExternalStream(m.stream(), device=dev)
+        xs = torch.cuda.Stream(device=dev)
+        stats, ms, wall = [], [], []
+        for s in range(n):
+            flush.fill_(s & 0xFF)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(ms_stream)
+            if host_input:
+                m.insert_pointcloud(h_scans[s].numpy(), org[s], DS_RES, FREE_RES, MAX_RANGE)
+            else:
+                m.insert_pointcloud(d_scans[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
+            ncoll = exchange(m, xs) if world > 1 else 0
+            st = m.last_stats()                    # D2H read-back of the scan counters happened inside the call
+            e1.record(ms_stream)
+            e1.synchronize()
+            barrier()
+            wall.append(time.perf_counter() - t0)
+            st["collectives"] = ncoll
+            stats.append(st)
+            ms.append(e0.elapsed_time(e1))
+        leaves = m.num_leaves()
+        m.close()
+        return stats, ms, wall, leaves
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor(x, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def reduce_sum_int(x):
+        if world == 1:
+            return x
+        t = torch.tensor(x, dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.tolist()
+
+    timed = list(range(a.warmup, n))
+    with ClockSampler(local) as clk:
+        st_d, ms_d, wall_d, leaves_d = run_pass(False)
+        st_h, ms_h, wall_h, leaves_h = run_pass(True)
+    clocks = clk.summary()
+    ms_d, ms_h = reduce_max(ms_d), reduce_max(ms_h)
+    # each rank counts the units of ITS shard; the whole-scan totals are the sums over ranks
+    upd = reduce_sum_int([s["voxel_updates"] for s in st_d])
+    vis = reduce_sum_int([s["voxel_visits"] for s in st_d])
+    pairs = reduce_sum_int([s["kernel_pairs"] for s in st_d])
+    pred_ms = reduce_max([float(s["predict_ms"]) for s in st_d])
+
+    if rank == 0:
+        T = sum(ms_d[s] for s in timed) * 1e-3
+        Th = sum(ms_h[s] for s in timed) * 1e-3
+        U = sum(upd[s] for s in timed)
+        V = sum(vis[s] for s in timed)
+        # ---- roofline of the dominant kernel (fused predict/update/prune), per launch
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        fp32 = ctypes.c_float(0)
+        la3dm_b200.load().la3dm_bench_fp32_peak(local, ctypes.byref(fp32))
+        k_ms = float(np.mean([pred_ms[s] for s in timed]))
+        k_bytes = float(np.mean([BYTES_PER_VISIT * vis[s] / world + BYTES_PER_MEMBER * st_d[s]["n_train"] +
+                                 BYTES_PER_TEST_BLOCK * st_d[s]["n_test_blocks"] / world for s in timed]))
+        k_flop = float(np.mean([FLOP_PER_PAIR * pairs[s] / world for s in timed]))
+        ach_gbs = k_bytes / (k_ms * 1e-3) / 1e9
+        ach_tf = k_flop / (k_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": U / T, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * T / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, {"parallelism": "blocks%d" % world if world > 1 else "single"}),
+            "voxel_visits_per_s": V / T,
+            "units_per_step": {"voxel_updates": U / a.steps, "voxel_visits": V / a.steps,
+                               "kernel_pairs": sum(pairs[s] for s in timed) / a.steps,
+                               "n_train": float(np.mean([st_d[s]["n_train"] for s in timed])),
+                               "n_test_blocks": float(np.mean([st_d[s]["n_test_blocks"] for s in timed]))},
+            "e2e": {"value": U / Th, "unit": UNIT, "ms_per_step": 1e3 * Th / a.steps,
+                    "wall_ms_per_step": 1e3 * float(np.mean([wall_h[s] for s in timed])),
+                    "h2d_bytes_per_step": int(a.points * 12),
+                    "d2h_bytes_per_step": int(np.mean([st_h[s]["d2h_bytes"] for s in timed])),
+                    "api": "la3dm_insert_pointcloud (pinned host cloud) + la3dm_last_stats"},
+            "gpu_launches": int(sum(st_d[s]["kernel_launches"] for s in timed)),
+            "collectives_per_step": st_d[timed[0]]["collectives"],
+            "roofline": {"kernel": "k_predict_bgk (fused predict + Occupancy::update + prune)", "bound": "hbm",
+                         "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "kernel_share_of_step": k_ms / (1e3 * T / a.steps), "algorithmic_bytes": k_bytes,
+                         "note": "the pair loop is fp32-pipe bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
+            "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": float(fp32.value), "unit": "TFLOP/s",
+                              "frac": ach_tf / fp32.value if fp32.value > 0 else None,
+                              "flop_per_pair": FLOP_PER_PAIR,
+                              "peak_source": "la3dm_bench_fp32_peak: register-resident FMA loop, measured in this run"},
+            "clocks": clocks,
+            "final_leaves": leaves_d,
+        }
+        fx = load_unit_fixture(a, n)
+        if fx is not None and world == 1:
+            line["units_match_oracle_fixture"] = bool(
+                all(fx[s]["voxel_visits"] == vis[s] and abs(fx[s]["voxel_updates"] - upd[s]) <= max(2, upd[s] // 5000)
+                    for s in range(n)))
+        if not a.no_cpu_baseline and world == 1:
+            ns = min(a.cpu_sample_scans, n)
+            if ref_available():
+                secs, cores = time_reference(pts, org, list(range(1, ns)), 1)
+                kind = "reference"
+            else:
+                from oracle.port import PortMap
+                o = PortMap("bgk", dict(BGK))
+                secs, cores, kind = [], 1, "port"
+                for s in range(ns):
+                    t0 = time.perf_counter()
+                    o.insert_pointcloud(pts[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
+                    if s >= 1:
+                        secs.append(time.perf_counter() - t0)
+            cu = sum(upd[s] for s in range(1, ns))
+            line["cpu_baseline"] = {"value": cu / sum(secs), "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "scans 1..%d of the same sequence into a fresh map after 1 untimed scan "
+                                              "(oracle/_ref fast flavour: the reference's own sources, -O3 AVX2, OpenMP)"
+                                              % (ns - 1),
+                                    "ms_per_scan": 1e3 * sum(secs) / len(secs), "host_cpus": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

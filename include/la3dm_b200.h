@@ -1,0 +1,195 @@
+/*
+ * la3dm_b200 -- C ABI of the B200-native per-scan Bayesian kernel occupancy update.
+ *
+ * This header is the drop-in boundary for ONE path of RobustFieldAutonomyLab/la3dm: the insert_pointcloud() call of
+ * BGKOctoMap / BGKLOctoMap / BGKLVOctoMap / GPOctoMap and the read side the ROS nodes use right after it.  The
+ * reference has no FFI layer of its own (it is a C++ class called from the nodes); each entry point below cites the
+ * reference member it replaces.  The C++ facade in include/la3dm_b200/ (same class and method names as the reference)
+ * forwards to these functions; INTEGRATION.md shows how a maintainer wires it into the existing nodes.
+ *
+ * Plain C: pointers + sizes only, no C++/torch types, no exceptions across the boundary.  All functions return
+ * LA3DM_OK (0) or a negative la3dm_status; la3dm_last_error() gives the text for the failing call on that map.
+ * A map is bound to one CUDA device and must be used from one host thread at a time (the reference's callers are
+ * single-threaded: src/bgkoctomap/bgkoctomap_server.cpp:195-204).
+ */
+#ifndef LA3DM_B200_H
+#define LA3DM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LA3DM_B200_ABI_VERSION 1
+
+typedef struct la3dm_map la3dm_map; /* opaque handle */
+
+typedef enum la3dm_method {
+    LA3DM_BGK = 0,   /* la3dm::BGKOctoMap   (include/bgkoctomap/bgkoctomap.h)    */
+    LA3DM_BGKL = 1,  /* la3dm::BGKLOctoMap  (include/bgkloctomap/bgkloctomap.h)  */
+    LA3DM_BGKLV = 2, /* la3dm::BGKLVOctoMap (include/bgklvoctomap/bgklvoctomap.h) */
+    LA3DM_GP = 3     /* la3dm::GPOctoMap    (include/gpoctomap/gpoctomap.h)      */
+} la3dm_method;
+
+typedef enum la3dm_status {
+    LA3DM_OK = 0,
+    LA3DM_ERR_INVALID = -1,     /* bad argument                                        */
+    LA3DM_ERR_CUDA = -2,        /* CUDA runtime failure (see la3dm_last_error)         */
+    LA3DM_ERR_UNSUPPORTED = -3, /* method / parameter combination not implemented      */
+    LA3DM_ERR_EXTENT = -4,      /* scan bounding box too large for the block-id space  */
+    LA3DM_ERR_NOMEM = -5,
+    LA3DM_ERR_NO_DEVICE = -6    /* no CUDA device: there is NO CPU fallback by design   */
+} la3dm_status;
+
+/* Node states: enum class State in include/bgkoctomap/bgkoctree_node.h:10-12.  BGKLV inserts UNCERTAIN before PRUNED
+ * (include/bgklvoctomap/bgklvoctree_node.h:11-13); la3dm_export_* always reports the numbering of the map's method. */
+enum { LA3DM_FREE = 0, LA3DM_OCCUPIED = 1, LA3DM_UNKNOWN = 2, LA3DM_PRUNED = 3 };
+enum { LA3DM_LV_UNCERTAIN = 3, LA3DM_LV_PRUNED = 4 };
+
+/* Constructor arguments of the four reference map classes (the reference keeps them in class statics:
+ * src/bgkoctomap/bgkoctomap.cpp:42-55).  Unused fields for a method are ignored. */
+typedef struct la3dm_params {
+    float resolution;        /* all: finest voxel edge (m)                                            */
+    int32_t block_depth;     /* all: test-data octree depth; block edge = 2^(depth-1) * resolution   */
+    float sf2;               /* all: kernel signal variance                                           */
+    float ell;               /* all: kernel length scale                                              */
+    float free_thresh;       /* all                                                                   */
+    float occupied_thresh;   /* all                                                                   */
+    float var_thresh;        /* BGK, BGKL, BGKLV                                                      */
+    float prior_A;           /* BGK, BGKL, BGKLV                                                      */
+    float prior_B;           /* BGK, BGKL, BGKLV                                                      */
+    int32_t original_size;   /* BGKLV (bool)                                                          */
+    float min_W;             /* BGKLV                                                                 */
+    float noise;             /* GP                                                                    */
+    float l;                 /* GP                                                                    */
+    float min_var;           /* GP                                                                    */
+    float max_var;           /* GP                                                                    */
+    float max_known_var;     /* GP                                                                    */
+} la3dm_params;
+
+/* One octree node in the reference's own in-memory layout: class Occupancy { bool classified; float m_A; float m_B;
+ * State state; } = 16 bytes (include/bgkoctomap/bgkoctree_node.h:76-81).  For GP the floats are (m_ivar, ivar)
+ * (include/gpoctomap/gpoctree_node.h). */
+typedef struct la3dm_node {
+    uint8_t classified;
+    uint8_t _pad0[3];
+    float a;
+    float b;
+    uint8_t state;
+    uint8_t _pad1[3];
+} la3dm_node;
+
+/* One leaf as LeafIterator exposes it (include/bgkoctomap/bgkoctomap.h:217-307: get_loc / get_size / get_node). */
+typedef struct la3dm_leaf {
+    int64_t block_key;  /* BlockHashKey (src/bgkoctomap/bgkblock.cpp:73-77)                      */
+    int32_t depth;      /* node depth in the block's octree, 0 = whole block                     */
+    int32_t index;      /* node index within its layer (child i of node k is 8k+i)               */
+    float x, y, z;      /* centre (Block::get_loc)                                               */
+    float size;         /* edge length (Block::get_size)                                         */
+    float a, b;         /* (m_A, m_B) or, for GP, (m_ivar, ivar)                                 */
+    float prob;         /* Occupancy::get_prob()                                                 */
+    float var;          /* Occupancy::get_var()                                                  */
+    uint8_t state;
+    uint8_t classified;
+    uint8_t _pad[6];    /* sizeof(la3dm_leaf) == 56 */
+} la3dm_leaf;
+
+/* Counters of the last insert call (the reference only prints some of these under -DDEBUG:
+ * src/bgkoctomap/bgkoctomap.cpp:226,286-287). */
+typedef struct la3dm_scan_stats {
+    int64_t n_points;        /* input points                                                         */
+    int64_t n_hits;          /* hits kept after downsampling and the range filter                    */
+    int64_t n_train;         /* training entries (hits + free samples / markers)                     */
+    int64_t n_data_blocks;   /* blocks that hold >= 1 training entry                                 */
+    int64_t n_test_blocks;   /* blocks predicted this scan                                           */
+    int64_t voxel_visits;    /* leaves of test blocks processed                                      */
+    int64_t voxel_updates;   /* visits for which Occupancy::update fired at least once               */
+    int64_t kernel_pairs;    /* (leaf, training entry) kernel evaluations the reference would do     */
+    int64_t n_blocks_total;  /* blocks in the map after the call                                     */
+    int64_t new_blocks;      /* blocks created by this call                                          */
+    int32_t kernel_launches; /* GPU kernels launched by this call (ours + CUB primitives)            */
+    int32_t grid_irregular;  /* 1 if the float-stepped block grid skipped or repeated an index       */
+    float device_ms;         /* device time of the call, CUDA events on the map's stream             */
+    float predict_ms;        /* device time of the fused predict/update/prune kernel alone           */
+    int64_t h2d_bytes;       /* bytes copied host -> device by this call (the cloud)                  */
+    int64_t d2h_bytes;       /* bytes copied device -> host by this call (counters)                   */
+} la3dm_scan_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+/* Replaces the map constructors (include/bgkoctomap/bgkoctomap.h:50-58, bgkloctomap.h:53-61, bgklvoctomap.h:52-62,
+ * gpoctomap.h:50-52).  device = CUDA ordinal.  Fails with LA3DM_ERR_NO_DEVICE when no GPU is present. */
+int la3dm_create(int method, const la3dm_params *params, int device, la3dm_map **out);
+int la3dm_destroy(la3dm_map *map);
+const char *la3dm_last_error(const la3dm_map *map);
+const char *la3dm_status_string(int status);
+int la3dm_abi_version(void);
+
+/* ---- the hot path -------------------------------------------------------------------------------------------- */
+/* Replaces  void insert_pointcloud(const PCLPointCloud &cloud, const point3f &origin, float ds_resolution,
+ *                                  float free_res = 2.0f, float max_range = -1)
+ * (include/bgkoctomap/bgkoctomap.h:82-84; src/bgkoctomap/bgkoctomap.cpp:214-366 and the -L/-LV/GP copies).
+ * xyz: HOST pointer to n points, x y z as float32 at the start of each stride_bytes-sized record (12 for packed xyz,
+ * 16 for pcl::PointXYZ).  The cloud is not retained.  Synchronous: the map is up to date on return. */
+int la3dm_insert_pointcloud(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, const float origin[3],
+                            float ds_resolution, float free_res, float max_range);
+
+/* Same, with the scan already resident in device memory of the map's device (no host<->device copy of the cloud).
+ * Work is enqueued on the map's stream; returns after the scan has been fully applied. */
+int la3dm_insert_pointcloud_device(la3dm_map *map, const float *d_xyz, size_t n, size_t stride_bytes,
+                                   const float origin[3], float ds_resolution, float free_res, float max_range);
+
+/* Front-end only: get_training_data() (src/bgkoctomap/bgkoctomap.cpp:383-417).  Runs the GPU front-end on a HOST
+ * cloud and returns the training set; does not touch the map.  Call with out == NULL to get the count.
+ * out: 7 floats per entry (x0 y0 z0 x1 y1 z1 label); for BGK/GP x1..z1 repeat x0..z0. */
+int la3dm_training_data(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, const float origin[3],
+                        float ds_resolution, float free_res, float max_range, float *out, size_t capacity,
+                        size_t *n_out);
+
+int la3dm_last_stats(const la3dm_map *map, la3dm_scan_stats *out);
+
+/* ---- read side ----------------------------------------------------------------------------------------------- */
+int64_t la3dm_num_blocks(const la3dm_map *map);
+int32_t la3dm_nodes_per_block(const la3dm_map *map); /* (8^depth - 1) / 7 */
+
+/* Whole map in the reference's Block/OcTree layout, for the host mirror behind begin_leaf()/search():
+ * keys[i] = BlockHashKey; nodes[i * nodes_per_block + off(d) + index], off(d) = (8^d - 1)/7, is node_arr[d][index]
+ * (src/bgkoctomap/bgkoctree.cpp:18-27).  Blocks come sorted by key. */
+int la3dm_export_blocks(la3dm_map *map, int64_t *keys, la3dm_node *nodes, size_t capacity_blocks, size_t *n_blocks);
+
+/* All current leaves, compacted on the GPU (what the nodes walk with begin_leaf()..end_leaf():
+ * src/bgkoctomap/bgkoctomap_static_node.cpp:111-139).  Sorted by (block_key, depth, index). */
+int64_t la3dm_num_leaves(la3dm_map *map);
+int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t *n_out);
+
+/* get_bbox() (src/bgkoctomap/bgkoctomap.cpp:368-381). */
+int la3dm_get_bbox(la3dm_map *map, float lim_min[3], float lim_max[3]);
+
+/* Key helpers (src/bgkoctomap/bgkblock.cpp:69-101), evaluated with the map's block size. */
+int64_t la3dm_block_to_hash_key(const la3dm_map *map, float x, float y, float z);
+void la3dm_hash_key_to_block(const la3dm_map *map, int64_t key, float center[3]);
+void la3dm_get_extended_block(const la3dm_map *map, int64_t key, int64_t out7[7]);
+
+/* ---- multi-GPU: test blocks of one scan sharded over ranks ----------------------------------------------------- */
+/* Every rank holds a full replica of the map and runs the (cheap) front-end redundantly; rank r predicts the test
+ * blocks t with t % world == r.  After insert, each rank packs the node states of ITS blocks; the caller all-gathers
+ * the packed buffers (NCCL, e.g. torch.distributed.all_gather_into_tensor on device tensors) and every rank unpacks
+ * the peers' rows, so that all replicas are identical again.  Buffers are DEVICE pointers. */
+int la3dm_set_shard(la3dm_map *map, int rank, int world);
+int64_t la3dm_shard_row_bytes(const la3dm_map *map);             /* bytes per packed block                 */
+int64_t la3dm_shard_rows(const la3dm_map *map);                  /* rows per rank = ceil(T / world)         */
+int la3dm_shard_pack(la3dm_map *map, void *d_rows);              /* writes la3dm_shard_rows() rows          */
+int la3dm_shard_unpack(la3dm_map *map, const void *d_all_rows);  /* reads world * la3dm_shard_rows() rows   */
+void *la3dm_stream(la3dm_map *map);                              /* cudaStream_t the map enqueues on        */
+
+/* ---- measurement helper -------------------------------------------------------------------------------------- */
+/* FP32 FMA throughput of `device` (TFLOP/s, 2 flop per FMA) from a register-resident FMA loop timed with CUDA
+ * events: the denominator for the fp32-pipe roofline of the predict kernel (SURVEY.md section 8d asks for it to be
+ * measured on the box).  Not part of the reference's API. */
+int la3dm_bench_fp32_peak(int device, float *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LA3DM_B200_H */

@@ -1,0 +1,358 @@
+// la3dm_b200 -- map lifetime, the per-scan driver and the read side (export of blocks / leaves).
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "engine.cuh"
+
+namespace la3dm_b200 {
+
+namespace {
+constexpr int kThreads = 256;
+
+__global__ void k_zero_counters(ScanCounters *c) { *c = ScanCounters(); }
+
+// state numbering differs for BGKLV only in the PRUNED slot; bits: 0..2 state, 7 classified
+__global__ void k_pack_nodes(const float2 *__restrict__ ab, const unsigned char *__restrict__ st,
+                             const unsigned int *__restrict__ order, unsigned int n_blocks, int nodes, int nodes_pad,
+                             la3dm_node *out) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t) n_blocks * nodes) return;
+    const unsigned int b = (unsigned int) (i / nodes), n = (unsigned int) (i % nodes);
+    const unsigned int slot = order[b];
+    const float2 v = ab[(size_t) slot * nodes + n];
+    const unsigned char s = st[(size_t) slot * nodes_pad + n];
+    la3dm_node o;
+    o.classified = s >> 7; o._pad0[0] = o._pad0[1] = o._pad0[2] = 0;
+    o.a = v.x; o.b = v.y;
+    o.state = s & 7; o._pad1[0] = o._pad1[1] = o._pad1[2] = 0;
+    out[i] = o;
+}
+
+__global__ void k_iota(unsigned int *v, unsigned int n) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
+__global__ void k_gather_keys(const long long *__restrict__ keys, const unsigned int *__restrict__ order,
+                              unsigned int n, long long *out) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = keys[order[i]];
+}
+
+// is_leaf (src/bgkoctomap/bgkoctree.cpp:72-82) on the packed state bytes
+__device__ inline bool node_is_leaf(const unsigned char *bst, const DevParams &P, int d, int i) {
+    if ((bst[P.layer_off[d] + i] & 7) == P.pruned_state) return false;
+    if (d + 1 < P.depth) return (bst[P.layer_off[d + 1] + 8 * i] & 7) == P.pruned_state;
+    return true;
+}
+
+__global__ void k_leaf_count(const unsigned char *__restrict__ st, const unsigned int *__restrict__ order,
+                             unsigned int n_blocks, const DevParams *__restrict__ Pg, int nodes_pad,
+                             unsigned int *cnt) {
+    // one warp per block
+    const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_blocks) return;
+    const DevParams &P = *Pg;
+    const unsigned char *bst = st + (size_t) order[w] * nodes_pad;
+    unsigned int c = 0;
+    for (int d = 0; d < P.depth; ++d) {
+        const int n = 1 << (3 * d);
+        for (int i = lane; i < n; i += 32) c += node_is_leaf(bst, P, d, i) ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[w] = c;
+}
+
+// leaves of one block in (depth, index) order
+__global__ void k_leaf_fill(const float2 *__restrict__ ab, const unsigned char *__restrict__ st,
+                            const long long *__restrict__ keys, const unsigned int *__restrict__ order,
+                            unsigned int n_blocks, const DevParams *__restrict__ Pg, const float3 *__restrict__ lut,
+                            int nodes_pad, const unsigned int *__restrict__ off, la3dm_leaf *out) {
+    const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_blocks) return;
+    const DevParams &P = *Pg;
+    const unsigned int slot = order[w];
+    const unsigned char *bst = st + (size_t) slot * nodes_pad;
+    const float2 *bab = ab + (size_t) slot * P.nodes;
+    const long long key = keys[slot];
+    const float cx = axis_center(key >> 40, P.block_size), cy = axis_center((key >> 20) & 0xFFFFF, P.block_size),
+                cz = axis_center(key & 0xFFFFF, P.block_size);
+    unsigned int base = off[w];
+    for (int d = 0; d < P.depth; ++d) {
+        const int n = 1 << (3 * d);
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool leaf = i < n && node_is_leaf(bst, P, d, i);
+            const unsigned int m = __ballot_sync(0xffffffffu, leaf);
+            if (leaf) {
+                const unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
+                const int node = P.layer_off[d] + i;
+                const float2 v = bab[node];
+                const unsigned char s = bst[node];
+                const float3 o = lut[node];
+                la3dm_leaf L;
+                L.block_key = key; L.depth = d; L.index = i;
+                L.x = o.x + cx; L.y = o.y + cy; L.z = o.z + cz;                       // Block::get_loc
+                L.size = (float) ((double) P.block_size / pow(2.0, (double) d));      // Block::get_size
+                L.a = v.x; L.b = v.y;
+                if (P.method == LA3DM_GP) {
+                    // gpoctree_node.cpp:31-34, gpoctree_node.h:60
+                    L.prob = 1.0f / (1.0f + (float) exp((double) (-P.l * v.x / P.max_ivar)));
+                    L.var = 1.0f / v.y;
+                } else {
+                    L.prob = v.x / (v.x + v.y);                                        // bgkoctree_node.cpp:27-29
+                    L.var = (v.x * v.y) / ((v.x + v.y) * (v.x + v.y) * (v.x + v.y + 1.0f));   // bgkoctree_node.h:60
+                }
+                L.state = s & 7; L.classified = s >> 7; for (int q = 0; q < 6; ++q) L._pad[q] = 0;
+                out[pos] = L;
+            }
+            base += __popc(m);
+        }
+    }
+}
+
+__global__ void k_leaf_total(const unsigned int *__restrict__ cnt, const unsigned int *__restrict__ off,
+                             unsigned int n, ScanCounters *c) {
+    c->n_leaves = n ? cnt[n - 1] + off[n - 1] : 0;
+}
+
+}  // namespace
+
+Map::~Map() {
+    if (d_params) cudaFree(d_params);
+    if (d_lut) cudaFree(d_lut);
+    if (d_nblocks) cudaFree(d_nblocks);
+    if (d_mm) cudaFree(d_mm);
+    if (d_grid) cudaFree(d_grid);
+    if (d_cnt) cudaFree(d_cnt);
+    if (h_cnt) cudaFreeHost(h_cnt);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (ev_p0) cudaEventDestroy(ev_p0);
+    if (ev_p1) cudaEventDestroy(ev_p1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Map::init(int method, const la3dm_params &p, int dev) {
+    if (method < LA3DM_BGK || method > LA3DM_GP) throw StatusError{LA3DM_ERR_INVALID, "unknown method"};
+    if (p.block_depth < 1 || p.block_depth > kMaxDepth) throw StatusError{LA3DM_ERR_INVALID, "block_depth out of range"};
+    if (!(p.resolution > 0) || !(p.ell > 0)) throw StatusError{LA3DM_ERR_INVALID, "resolution and ell must be > 0"};
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        throw StatusError{LA3DM_ERR_NO_DEVICE, "no CUDA device (la3dm_b200 has no CPU fallback)"};
+    }
+    if (dev < 0 || dev >= ndev) throw StatusError{LA3DM_ERR_INVALID, "device ordinal out of range"};
+    device = dev;
+    LA3DM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LA3DM_CUDA(cudaGetDeviceProperties(&prop, device));
+    num_sms = prop.multiProcessorCount;
+    LA3DM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    LA3DM_CUDA(cudaEventCreate(&ev0));
+    LA3DM_CUDA(cudaEventCreate(&ev1));
+    LA3DM_CUDA(cudaEventCreate(&ev_p0));
+    LA3DM_CUDA(cudaEventCreate(&ev_p1));
+
+    api_params = p;
+    DevParams &h = hp;
+    std::memset(&h, 0, sizeof(h));
+    h.method = method;
+    h.depth = p.block_depth;
+    int off = 0, n = 1;
+    for (int d = 0; d < h.depth; ++d, n *= 8) { h.layer_off[d] = off; off += n; }
+    h.layer_off[h.depth] = off;
+    h.nodes = off;
+    h.finest = n / 8;
+    h.resolution = p.resolution;
+    // block_size((float) pow(2, block_depth - 1) * resolution)   (src/bgkoctomap/bgkoctomap.cpp:41)
+    h.block_size = (float) std::pow(2, p.block_depth - 1) * p.resolution;
+    h.half_size = h.block_size / 2.0f;
+    h.sf2 = p.sf2; h.ell = p.ell;
+    h.free_thresh = p.free_thresh; h.occupied_thresh = p.occupied_thresh; h.var_thresh = p.var_thresh;
+    h.prior_A = p.prior_A; h.prior_B = p.prior_B;
+    h.min_W = p.min_W; h.original_size = p.original_size;
+    h.noise = p.noise; h.l = p.l;
+    if (method == LA3DM_GP) {   // src/gpoctomap/gpoctomap.cpp:38-40
+        h.min_ivar = 1.0f / p.max_var; h.max_ivar = 1.0f / p.min_var; h.min_known_ivar = 1.0f / p.max_known_var;
+        h.def_a = 0.0f; h.def_b = h.min_ivar;                       // gpoctree_node.h:34
+    } else {
+        h.def_a = p.prior_A; h.def_b = p.prior_B;                   // bgkoctree_node.h:34
+    }
+    h.pruned_state = method == LA3DM_BGKLV ? LA3DM_LV_PRUNED : LA3DM_PRUNED;
+    nodes_pad = (h.nodes + 15) / 16 * 16;
+
+    // node-centre look-up table: init_key_loc_map (src/bgkoctomap/bgkblock.cpp:7-32), breadth first, child i of a
+    // node gets +-quarter-edge offsets from bits 4 (x), 2 (y), 1 (z) of i, with the reference's float/double mix
+    h_lut.assign(h.nodes, make_float3(0.f, 0.f, 0.f));
+    for (int d = 0; d + 1 < h.depth; ++d) {
+        const float half_size = (float) (p.resolution * std::pow(2, h.depth - d - 1) * 0.5f);
+        const int cnt = 1 << (3 * d);
+        for (int idx = 0; idx < cnt; ++idx) {
+            const float3 c = h_lut[h.layer_off[d] + idx];
+            for (int i = 0; i < 8; ++i) {
+                float3 ch;
+                ch.x = (float) (c.x + half_size * (i & 4 ? 0.5 : -0.5));
+                ch.y = (float) (c.y + half_size * (i & 2 ? 0.5 : -0.5));
+                ch.z = (float) (c.z + half_size * (i & 1 ? 0.5 : -0.5));
+                h_lut[h.layer_off[d + 1] + idx * 8 + i] = ch;
+            }
+        }
+    }
+    LA3DM_CUDA(cudaMalloc(&d_params, sizeof(DevParams)));
+    LA3DM_CUDA(cudaMemcpy(d_params, &h, sizeof(DevParams), cudaMemcpyHostToDevice));
+    LA3DM_CUDA(cudaMalloc(&d_lut, sizeof(float3) * h.nodes));
+    LA3DM_CUDA(cudaMemcpy(d_lut, h_lut.data(), sizeof(float3) * h.nodes, cudaMemcpyHostToDevice));
+    LA3DM_CUDA(cudaMalloc(&d_nblocks, sizeof(unsigned int)));
+    LA3DM_CUDA(cudaMemset(d_nblocks, 0, sizeof(unsigned int)));
+    LA3DM_CUDA(cudaMalloc(&d_mm, sizeof(unsigned int) * 18));
+    LA3DM_CUDA(cudaMalloc(&d_grid, sizeof(GridDesc)));
+    LA3DM_CUDA(cudaMalloc(&d_cnt, sizeof(ScanCounters)));
+    LA3DM_CUDA(cudaMemset(d_cnt, 0, sizeof(ScanCounters)));
+    LA3DM_CUDA(cudaMallocHost(&h_cnt, sizeof(ScanCounters)));
+    std::memset(h_cnt, 0, sizeof(ScanCounters));
+    ensure_pool(4096);
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Map::read_counters() {
+    d2h_bytes += sizeof(ScanCounters);
+    LA3DM_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(ScanCounters), cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
+                        float max_range, bool frontend_only) {
+    if (stride_bytes < 12 || stride_bytes % 4 != 0) throw StatusError{LA3DM_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 12"};
+    if (n > 0x7FFFFFF0ull) throw StatusError{LA3DM_ERR_INVALID, "too many points"};
+    if (n > 0 && !d_xyz) throw StatusError{LA3DM_ERR_INVALID, "null cloud"};
+    if (!(fr > 0)) throw StatusError{LA3DM_ERR_INVALID, "free_res must be > 0"};
+    if (hp.method != LA3DM_BGK && hp.method != LA3DM_GP)
+        throw StatusError{LA3DM_ERR_UNSUPPORTED, "method not implemented on the GPU yet"};
+    LA3DM_CUDA(cudaSetDevice(device));
+    launches = 0;
+    d2h_bytes = 0;
+    std::memset(&stats, 0, sizeof(stats));
+    stats.n_points = (int64_t) n;
+    LA3DM_CUDA(cudaEventRecord(ev0, stream));
+    k_zero_counters<<<1, 1, 0, stream>>>(d_cnt);
+    ++launches;
+    std::memset(h_cnt, 0, sizeof(ScanCounters));
+    last_T = 0;
+    bool predicted = false;
+
+    frontend_bgk(d_xyz, (unsigned int) n, (int) (stride_bytes / 4), make_float3(origin[0], origin[1], origin[2]), ds,
+                 fr, max_range);
+    // empty training set: nothing to do (src/bgkoctomap/bgkoctomap.cpp:230-232)
+    if (!frontend_only && h_cnt->n_hits > 0) {
+        bin_and_plan();
+        if (last_T > 0) { predict(); predicted = true; }
+    }
+    LA3DM_CUDA(cudaEventRecord(ev1, stream));
+    read_counters();
+    LA3DM_CUDA(cudaMemcpy(&h_cnt->pad, d_nblocks, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    n_blocks = h_cnt->pad;
+    last_T = frontend_only ? 0 : h_cnt->n_test_blocks;
+    stats.n_hits = h_cnt->n_hits;
+    stats.n_train = h_cnt->n_train;
+    stats.n_data_blocks = h_cnt->n_data_blocks;
+    stats.n_test_blocks = h_cnt->n_test_blocks;
+    stats.voxel_visits = (int64_t) h_cnt->visits;
+    stats.voxel_updates = (int64_t) h_cnt->updates;
+    stats.kernel_pairs = (int64_t) h_cnt->pairs;
+    stats.n_blocks_total = n_blocks;
+    stats.new_blocks = h_cnt->n_new_blocks;
+    stats.kernel_launches = launches;
+    d2h_bytes += sizeof(unsigned int);
+    stats.h2d_bytes = h2d_bytes;      // set by the host entry point (0 for a device-resident cloud)
+    stats.d2h_bytes = d2h_bytes;
+    h2d_bytes = 0;
+    float ms = 0.f;
+    LA3DM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    stats.device_ms = ms;
+    if (predicted) { LA3DM_CUDA(cudaEventElapsedTime(&ms, ev_p0, ev_p1)); stats.predict_ms = ms; }
+}
+
+// slots sorted by block key (deterministic export order)
+void Map::sorted_block_order(DevBuf &order, size_t n) {
+    for (int i = 0; i < 2; ++i) { order_keys[i].reserve(n * 8, stream); order_vals[i].reserve(n * 4, stream); }
+    LA3DM_CUDA(cudaMemcpyAsync(order_keys[0].p, keys.p, n * 8, cudaMemcpyDeviceToDevice, stream));
+    k_iota<<<ceil_div((long long) n, kThreads), kThreads, 0, stream>>>(order_vals[0].as<unsigned int>(), (unsigned int) n);
+    cub::DoubleBuffer<long long> dk(order_keys[0].as<long long>(), order_keys[1].as<long long>());
+    cub::DoubleBuffer<unsigned int> dv(order_vals[0].as<unsigned int>(), order_vals[1].as<unsigned int>());
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int) n, 0, 60, stream);
+    cub_tmp.reserve(tmp, stream);
+    LA3DM_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, dk, dv, (int) n, 0, 60, stream));
+    order.reserve(n * 4, stream);
+    LA3DM_CUDA(cudaMemcpyAsync(order.p, dv.Current(), n * 4, cudaMemcpyDeviceToDevice, stream));
+}
+
+void Map::export_blocks(int64_t *out_keys, la3dm_node *out_nodes, size_t cap, size_t *n_out) {
+    LA3DM_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t) n_blocks;
+    if (n_out) *n_out = n;
+    if (n == 0 || (!out_keys && !out_nodes)) return;
+    if (cap < n) throw StatusError{LA3DM_ERR_INVALID, "export_blocks: capacity too small"};
+    sorted_block_order(block_order, n);
+    const unsigned int *order = block_order.as<unsigned int>();
+    if (out_keys) {
+        export_buf.reserve(n * 8, stream);
+        k_gather_keys<<<ceil_div((long long) n, kThreads), kThreads, 0, stream>>>(keys.as<long long>(), order,
+                                                                                  (unsigned int) n,
+                                                                                  export_buf.as<long long>());
+        LA3DM_CUDA(cudaMemcpyAsync(out_keys, export_buf.p, n * 8, cudaMemcpyDeviceToHost, stream));
+        LA3DM_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (out_nodes) {
+        const size_t total = n * (size_t) hp.nodes;
+        export_buf.reserve(total * sizeof(la3dm_node), stream);
+        k_pack_nodes<<<ceil_div((long long) total, kThreads), kThreads, 0, stream>>>(
+            ab.as<float2>(), st.as<unsigned char>(), order, (unsigned int) n, hp.nodes, nodes_pad,
+            export_buf.as<la3dm_node>());
+        LA3DM_CUDA(cudaMemcpyAsync(out_nodes, export_buf.p, total * sizeof(la3dm_node), cudaMemcpyDeviceToHost,
+                                   stream));
+        LA3DM_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
+long long Map::count_leaves() {
+    LA3DM_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t) n_blocks;
+    if (n == 0) return 0;
+    sorted_block_order(block_order, n);
+    const unsigned int *order = block_order.as<unsigned int>();
+    leaf_cnt.reserve(n * 4, stream);
+    leaf_off.reserve(n * 4, stream);
+    k_leaf_count<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
+        st.as<unsigned char>(), order, (unsigned int) n, d_params, nodes_pad, leaf_cnt.as<unsigned int>());
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (int) n, stream);
+    cub_tmp.reserve(tmp, stream);
+    LA3DM_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(),
+                                             (int) n, stream));
+    k_leaf_total<<<1, 1, 0, stream>>>(leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (unsigned int) n, d_cnt);
+    unsigned int total = 0;
+    LA3DM_CUDA(cudaMemcpyAsync(&total, &d_cnt->n_leaves, 4, cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    return total;
+}
+
+void Map::export_leaves(la3dm_leaf *out, size_t cap, size_t *n_out) {
+    const long long total = count_leaves();   // leaves block_order (= key order) / leaf_off ready
+    if (n_out) *n_out = (size_t) total;
+    if (!out || total == 0) return;
+    if (cap < (size_t) total) throw StatusError{LA3DM_ERR_INVALID, "export_leaves: capacity too small"};
+    const size_t n = (size_t) n_blocks;
+    leaf_out.reserve((size_t) total * sizeof(la3dm_leaf), stream);
+    k_leaf_fill<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
+        ab.as<float2>(), st.as<unsigned char>(), keys.as<long long>(), block_order.as<unsigned int>(), (unsigned int) n,
+        d_params, d_lut, nodes_pad, leaf_off.as<unsigned int>(), leaf_out.as<la3dm_leaf>());
+    LA3DM_CUDA(cudaMemcpyAsync(out, leaf_out.p, (size_t) total * sizeof(la3dm_leaf), cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace la3dm_b200
