@@ -12,18 +12,15 @@ namespace la3dm_b200 {
 namespace {
 constexpr int kThreads = 256;
 
-__global__ void k_zero_counters(ScanCounters *c) { *c = ScanCounters(); }
-
 // state numbering differs for BGKLV only in the PRUNED slot; bits: 0..2 state, 7 classified
-__global__ void k_pack_nodes(const float2 *__restrict__ ab, const unsigned char *__restrict__ st,
-                             const unsigned int *__restrict__ order, unsigned int n_blocks, int nodes, int nodes_pad,
-                             la3dm_node *out) {
+__global__ void k_pack_nodes(const unsigned char *__restrict__ pool, const unsigned int *__restrict__ order,
+                             unsigned int n_blocks, int nodes, int st_off, int rec_bytes, la3dm_node *out) {
     const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t) n_blocks * nodes) return;
     const unsigned int b = (unsigned int) (i / nodes), n = (unsigned int) (i % nodes);
-    const unsigned int slot = order[b];
-    const float2 v = ab[(size_t) slot * nodes + n];
-    const unsigned char s = st[(size_t) slot * nodes_pad + n];
+    const unsigned char *rec = pool + (size_t) order[b] * rec_bytes;
+    const float2 v = reinterpret_cast<const float2 *>(rec)[n];
+    const unsigned char s = rec[st_off + n];
     la3dm_node o;
     o.classified = s >> 7; o._pad0[0] = o._pad0[1] = o._pad0[2] = 0;
     o.a = v.x; o.b = v.y;
@@ -49,14 +46,13 @@ __device__ inline bool node_is_leaf(const unsigned char *bst, const DevParams &P
     return true;
 }
 
-__global__ void k_leaf_count(const unsigned char *__restrict__ st, const unsigned int *__restrict__ order,
-                             unsigned int n_blocks, const DevParams *__restrict__ Pg, int nodes_pad,
-                             unsigned int *cnt) {
+__global__ void k_leaf_count(const unsigned char *__restrict__ pool, const unsigned int *__restrict__ order,
+                             unsigned int n_blocks, const DevParams *__restrict__ Pg, unsigned int *cnt) {
     // one warp per block
     const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_blocks) return;
     const DevParams &P = *Pg;
-    const unsigned char *bst = st + (size_t) order[w] * nodes_pad;
+    const unsigned char *bst = pool + (size_t) order[w] * P.rec_bytes + P.st_off;
     unsigned int c = 0;
     for (int d = 0; d < P.depth; ++d) {
         const int n = 1 << (3 * d);
@@ -67,16 +63,17 @@ __global__ void k_leaf_count(const unsigned char *__restrict__ st, const unsigne
 }
 
 // leaves of one block in (depth, index) order
-__global__ void k_leaf_fill(const float2 *__restrict__ ab, const unsigned char *__restrict__ st,
-                            const long long *__restrict__ keys, const unsigned int *__restrict__ order,
-                            unsigned int n_blocks, const DevParams *__restrict__ Pg, const float3 *__restrict__ lut,
-                            int nodes_pad, const unsigned int *__restrict__ off, la3dm_leaf *out) {
+__global__ void k_leaf_fill(const unsigned char *__restrict__ pool, const long long *__restrict__ keys,
+                            const unsigned int *__restrict__ order, unsigned int n_blocks,
+                            const DevParams *__restrict__ Pg, const float3 *__restrict__ lut,
+                            const unsigned int *__restrict__ off, la3dm_leaf *out) {
     const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_blocks) return;
     const DevParams &P = *Pg;
     const unsigned int slot = order[w];
-    const unsigned char *bst = st + (size_t) slot * nodes_pad;
-    const float2 *bab = ab + (size_t) slot * P.nodes;
+    const unsigned char *rec = pool + (size_t) slot * P.rec_bytes;
+    const unsigned char *bst = rec + P.st_off;
+    const float2 *bab = reinterpret_cast<const float2 *>(rec);
     const long long key = keys[slot];
     const float cx = axis_center(key >> 40, P.block_size), cy = axis_center((key >> 20) & 0xFFFFF, P.block_size),
                 cz = axis_center(key & 0xFFFFF, P.block_size);
@@ -119,16 +116,25 @@ __global__ void k_leaf_total(const unsigned int *__restrict__ cnt, const unsigne
     c->n_leaves = n ? cnt[n - 1] + off[n - 1] : 0;
 }
 
+unsigned int grow_to(unsigned int need, unsigned int floor_) {
+    const unsigned long long w = (unsigned long long) need + need / 4 + 64;
+    return (unsigned int) std::min<unsigned long long>(std::max<unsigned long long>(w, floor_), 0x7FFFFFF0ull);
+}
+
 }  // namespace
 
+size_t radix_sort_temp_bytes(unsigned int items);   // frontend.cu
+
 Map::~Map() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (d_params) cudaFree(d_params);
     if (d_lut) cudaFree(d_lut);
-    if (d_nblocks) cudaFree(d_nblocks);
     if (d_mm) cudaFree(d_mm);
     if (d_grid) cudaFree(d_grid);
     if (d_cnt) cudaFree(d_cnt);
     if (h_cnt) cudaFreeHost(h_cnt);
+    if (d_args) cudaFree(d_args);
+    if (h_args) cudaFreeHost(h_args);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ev_p0) cudaEventDestroy(ev_p0);
@@ -156,6 +162,8 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     LA3DM_CUDA(cudaEventCreate(&ev1));
     LA3DM_CUDA(cudaEventCreate(&ev_p0));
     LA3DM_CUDA(cudaEventCreate(&ev_p1));
+    const char *env = getenv("LA3DM_NO_GRAPH");
+    use_graph = !(env && env[0] == '1');
 
     api_params = p;
     DevParams &h = hp;
@@ -167,6 +175,8 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     h.layer_off[h.depth] = off;
     h.nodes = off;
     h.finest = n / 8;
+    h.st_off = h.nodes * 8;
+    h.rec_bytes = (h.nodes * 9 + 15) / 16 * 16;
     h.resolution = p.resolution;
     // block_size((float) pow(2, block_depth - 1) * resolution)   (src/bgkoctomap/bgkoctomap.cpp:41)
     h.block_size = (float) std::pow(2, p.block_depth - 1) * p.resolution;
@@ -183,7 +193,6 @@ void Map::init(int method, const la3dm_params &p, int dev) {
         h.def_a = p.prior_A; h.def_b = p.prior_B;                   // bgkoctree_node.h:34
     }
     h.pruned_state = method == LA3DM_BGKLV ? LA3DM_LV_PRUNED : LA3DM_PRUNED;
-    nodes_pad = (h.nodes + 15) / 16 * 16;
 
     // node-centre look-up table: init_key_loc_map (src/bgkoctomap/bgkblock.cpp:7-32), breadth first, child i of a
     // node gets +-quarter-edge offsets from bits 4 (x), 2 (y), 1 (z) of i, with the reference's float/double mix
@@ -206,22 +215,62 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     LA3DM_CUDA(cudaMemcpy(d_params, &h, sizeof(DevParams), cudaMemcpyHostToDevice));
     LA3DM_CUDA(cudaMalloc(&d_lut, sizeof(float3) * h.nodes));
     LA3DM_CUDA(cudaMemcpy(d_lut, h_lut.data(), sizeof(float3) * h.nodes, cudaMemcpyHostToDevice));
-    LA3DM_CUDA(cudaMalloc(&d_nblocks, sizeof(unsigned int)));
-    LA3DM_CUDA(cudaMemset(d_nblocks, 0, sizeof(unsigned int)));
     LA3DM_CUDA(cudaMalloc(&d_mm, sizeof(unsigned int) * 18));
     LA3DM_CUDA(cudaMalloc(&d_grid, sizeof(GridDesc)));
     LA3DM_CUDA(cudaMalloc(&d_cnt, sizeof(ScanCounters)));
     LA3DM_CUDA(cudaMemset(d_cnt, 0, sizeof(ScanCounters)));
     LA3DM_CUDA(cudaMallocHost(&h_cnt, sizeof(ScanCounters)));
     std::memset(h_cnt, 0, sizeof(ScanCounters));
-    ensure_pool(4096);
+    LA3DM_CUDA(cudaMalloc(&d_args, sizeof(ScanArgs)));
+    LA3DM_CUDA(cudaMallocHost(&h_args, sizeof(ScanArgs)));
+    std::memset(h_args, 0, sizeof(ScanArgs));
+    // first guess of the per-scan capacities; they follow the scans from here on (grown on overflow, see insert_device)
+    caps.points = 4096;
+    caps.raw = 16 * caps.points;
+    caps.train = caps.points + caps.raw;
+    caps.members = caps.train + caps.train / 8;
+    caps.cells = 1u << 16;
+    caps.tests = 8192;
+    caps.vg_cells = 1u << 20;
+    ensure_pool(4096 + caps.tests);
+    ensure_workspace();
     LA3DM_CUDA(cudaStreamSynchronize(stream));
 }
 
-void Map::read_counters() {
-    d2h_bytes += sizeof(ScanCounters);
-    LA3DM_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(ScanCounters), cudaMemcpyDeviceToHost, stream));
-    LA3DM_CUDA(cudaStreamSynchronize(stream));
+void Map::invalidate_graph() {
+    if (graph_exec) {
+        cudaStreamSynchronize(stream);
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+    }
+}
+
+// buffers for the current `caps` (grow-only); any reallocation invalidates the captured graph
+void Map::ensure_workspace() {
+    caps.train = caps.points + caps.raw;
+    bool moved = false;
+    const size_t n_sort = std::max<size_t>(std::max(caps.points, caps.raw), caps.members);
+    for (int i = 0; i < 2; ++i) {
+        moved |= sort_keys[i].reserve(n_sort * 4, stream);
+        moved |= sort_vals[i].reserve(n_sort * 4, stream);
+    }
+    moved |= run_start.reserve((std::max<size_t>(caps.points, caps.raw) + 2) * 4, stream);
+    moved |= tiles.reserve((n_sort / kTile + (size_t) caps.cells / 32 / 256 + 16) * 8, stream);
+    moved |= long_list.reserve((size_t) 2 * kMaxLongRuns * 4, stream);
+    moved |= hit_cnt.reserve((size_t) caps.points * 4, stream);
+    moved |= hits_ds.reserve((size_t) caps.points * sizeof(float4), stream);
+    moved |= frees_raw.reserve((size_t) caps.raw * sizeof(float4), stream);
+    moved |= xy.reserve((size_t) caps.train * sizeof(float4), stream);
+    moved |= pts_sorted.reserve((size_t) caps.members * sizeof(float4), stream);
+    moved |= db_id.reserve(((size_t) caps.members + 2) * 4, stream);
+    moved |= db_start.reserve(((size_t) caps.members + 2) * 4, stream);
+    moved |= cell_db.reserve((size_t) caps.cells * 4, stream);
+    moved |= test_bits.reserve(((size_t) caps.cells / 32 + 2) * 4, stream);
+    moved |= test_id.reserve((size_t) caps.tests * 4, stream);
+    moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
+    const size_t tmp = radix_sort_temp_bytes((unsigned int) n_sort);
+    if (tmp > cub_tmp_bytes) { moved |= cub_tmp.reserve(tmp, stream); cub_tmp_bytes = tmp; }
+    if (moved) invalidate_graph();
 }
 
 void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
@@ -230,31 +279,77 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     if (n > 0x7FFFFFF0ull) throw StatusError{LA3DM_ERR_INVALID, "too many points"};
     if (n > 0 && !d_xyz) throw StatusError{LA3DM_ERR_INVALID, "null cloud"};
     if (!(fr > 0)) throw StatusError{LA3DM_ERR_INVALID, "free_res must be > 0"};
+    if (ds == 0) throw StatusError{LA3DM_ERR_INVALID, "ds_resolution must not be 0"};
     if (hp.method != LA3DM_BGK && hp.method != LA3DM_GP)
         throw StatusError{LA3DM_ERR_UNSUPPORTED, "method not implemented on the GPU yet"};
     LA3DM_CUDA(cudaSetDevice(device));
-    launches = 0;
     d2h_bytes = 0;
     std::memset(&stats, 0, sizeof(stats));
     stats.n_points = (int64_t) n;
-    LA3DM_CUDA(cudaEventRecord(ev0, stream));
-    k_zero_counters<<<1, 1, 0, stream>>>(d_cnt);
-    ++launches;
-    std::memset(h_cnt, 0, sizeof(ScanCounters));
     last_T = 0;
-    bool predicted = false;
 
-    frontend_bgk(d_xyz, (unsigned int) n, (int) (stride_bytes / 4), make_float3(origin[0], origin[1], origin[2]), ds,
-                 fr, max_range);
-    // empty training set: nothing to do (src/bgkoctomap/bgkoctomap.cpp:230-232)
-    if (!frontend_only && h_cnt->n_hits > 0) {
-        bin_and_plan();
-        if (last_T > 0) { predict(); predicted = true; }
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 12) throw StatusError{LA3DM_ERR_NOMEM, "scan workspace did not settle"};
+        if (n > caps.points) caps.points = grow_to((unsigned int) n, 4096);
+        ensure_workspace();
+        ensure_pool((size_t) n_blocks + caps.tests);
+
+        ScanArgs &a = *h_args;
+        a.xyz = d_xyz; a.n = (unsigned int) n; a.stride_f = (int) (stride_bytes / 4);
+        a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
+        a.ds = ds; a.inv_ds = 1.0f / ds; a.fr = fr; a.max_range = max_range;
+        a.free_label = hp.method == LA3DM_GP ? -1.0f : 0.0f;   // src/gpoctomap/gpoctomap.cpp:399
+        a.frontend_only = frontend_only ? 1 : 0;
+        a.shard_rank = shard_rank; a.shard_world = shard_world;
+        a.n_blocks = (unsigned int) n_blocks; a.pool_cap = (unsigned int) pool_cap;
+
+        LA3DM_CUDA(cudaEventRecord(ev0, stream));
+        LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));
+        if (use_graph) {
+            if (!graph_exec || !(graph_caps == caps) || graph_frontend_only != (int) frontend_only) {
+                invalidate_graph();
+                cudaGraph_t g = nullptr;
+                LA3DM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                try {
+                    enqueue_scan(frontend_only);
+                } catch (...) {
+                    cudaStreamEndCapture(stream, &g);
+                    if (g) cudaGraphDestroy(g);
+                    throw;
+                }
+                LA3DM_CUDA(cudaStreamEndCapture(stream, &g));
+                const cudaError_t e = cudaGraphInstantiate(&graph_exec, g, 0);
+                cudaGraphDestroy(g);
+                LA3DM_CUDA(e);
+                graph_caps = caps;
+                graph_frontend_only = (int) frontend_only;
+                graph_launches = launches;
+            }
+            LA3DM_CUDA(cudaGraphLaunch(graph_exec, stream));
+            launches = graph_launches;
+        } else {
+            enqueue_scan(frontend_only);
+        }
+        LA3DM_CUDA(cudaEventRecord(ev1, stream));
+        // the one synchronisation of the scan: counters (and overflow bits) back to the host
+        d2h_bytes += sizeof(ScanCounters);
+        LA3DM_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(ScanCounters), cudaMemcpyDeviceToHost, stream));
+        LA3DM_CUDA(cudaStreamSynchronize(stream));
+        const unsigned int ovf = h_cnt->overflow;
+        if (!ovf) break;
+        // a workspace was too small: nothing was written to the map; grow from the sizes the device reports and replay
+        ++replays;
+        if (ovf & OVF_EXTENT) throw StatusError{LA3DM_ERR_EXTENT, "scan bounding box spans too many blocks"};
+        if (ovf & OVF_VGCELLS) caps.vg_cells = grow_to(h_cnt->vg_cells_needed, 1u << 20);
+        if (ovf & OVF_RAW) caps.raw = grow_to(h_cnt->n_raw_frees, 1024);
+        if (ovf & OVF_CELLS) caps.cells = grow_to(h_cnt->n_cells, 1u << 16);
+        if (ovf & OVF_MEMBERS) caps.members = grow_to(h_cnt->n_members, 1024);
+        if (ovf & OVF_TESTS) caps.tests = grow_to(h_cnt->n_test_blocks, 8192);
+        caps.train = caps.points + caps.raw;
+        if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }
-    LA3DM_CUDA(cudaEventRecord(ev1, stream));
-    read_counters();
-    LA3DM_CUDA(cudaMemcpy(&h_cnt->pad, d_nblocks, sizeof(unsigned int), cudaMemcpyDeviceToHost));
-    n_blocks = h_cnt->pad;
+
+    n_blocks = frontend_only ? n_blocks : (long long) h_cnt->n_blocks;
     last_T = frontend_only ? 0 : h_cnt->n_test_blocks;
     stats.n_hits = h_cnt->n_hits;
     stats.n_train = h_cnt->n_train;
@@ -266,14 +361,17 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     stats.n_blocks_total = n_blocks;
     stats.new_blocks = h_cnt->n_new_blocks;
     stats.kernel_launches = launches;
-    d2h_bytes += sizeof(unsigned int);
-    stats.h2d_bytes = h2d_bytes;      // set by the host entry point (0 for a device-resident cloud)
+    stats.grid_irregular = (int32_t) h_cnt->grid_irregular;
+    stats.h2d_bytes = h2d_bytes + (long long) sizeof(ScanArgs);   // h2d_bytes: the cloud, set by the host entry point
     stats.d2h_bytes = d2h_bytes;
     h2d_bytes = 0;
     float ms = 0.f;
     LA3DM_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     stats.device_ms = ms;
-    if (predicted) { LA3DM_CUDA(cudaEventElapsedTime(&ms, ev_p0, ev_p1)); stats.predict_ms = ms; }
+    if (!frontend_only && h_cnt->n_train > 0) {
+        if (cudaEventElapsedTime(&ms, ev_p0, ev_p1) == cudaSuccess) stats.predict_ms = ms;
+        else cudaGetLastError();
+    }
 }
 
 // slots sorted by block key (deterministic export order)
@@ -285,8 +383,8 @@ void Map::sorted_block_order(DevBuf &order, size_t n) {
     cub::DoubleBuffer<unsigned int> dv(order_vals[0].as<unsigned int>(), order_vals[1].as<unsigned int>());
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int) n, 0, 60, stream);
-    cub_tmp.reserve(tmp, stream);
-    LA3DM_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, dk, dv, (int) n, 0, 60, stream));
+    export_tmp.reserve(tmp, stream);
+    LA3DM_CUDA(cub::DeviceRadixSort::SortPairs(export_tmp.p, tmp, dk, dv, (int) n, 0, 60, stream));
     order.reserve(n * 4, stream);
     LA3DM_CUDA(cudaMemcpyAsync(order.p, dv.Current(), n * 4, cudaMemcpyDeviceToDevice, stream));
 }
@@ -311,7 +409,7 @@ void Map::export_blocks(int64_t *out_keys, la3dm_node *out_nodes, size_t cap, si
         const size_t total = n * (size_t) hp.nodes;
         export_buf.reserve(total * sizeof(la3dm_node), stream);
         k_pack_nodes<<<ceil_div((long long) total, kThreads), kThreads, 0, stream>>>(
-            ab.as<float2>(), st.as<unsigned char>(), order, (unsigned int) n, hp.nodes, nodes_pad,
+            pool.as<unsigned char>(), order, (unsigned int) n, hp.nodes, hp.st_off, hp.rec_bytes,
             export_buf.as<la3dm_node>());
         LA3DM_CUDA(cudaMemcpyAsync(out_nodes, export_buf.p, total * sizeof(la3dm_node), cudaMemcpyDeviceToHost,
                                    stream));
@@ -328,11 +426,11 @@ long long Map::count_leaves() {
     leaf_cnt.reserve(n * 4, stream);
     leaf_off.reserve(n * 4, stream);
     k_leaf_count<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
-        st.as<unsigned char>(), order, (unsigned int) n, d_params, nodes_pad, leaf_cnt.as<unsigned int>());
+        pool.as<unsigned char>(), order, (unsigned int) n, d_params, leaf_cnt.as<unsigned int>());
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (int) n, stream);
-    cub_tmp.reserve(tmp, stream);
-    LA3DM_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(),
+    export_tmp.reserve(tmp, stream);
+    LA3DM_CUDA(cub::DeviceScan::ExclusiveSum(export_tmp.p, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(),
                                              (int) n, stream));
     k_leaf_total<<<1, 1, 0, stream>>>(leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (unsigned int) n, d_cnt);
     unsigned int total = 0;
@@ -349,8 +447,8 @@ void Map::export_leaves(la3dm_leaf *out, size_t cap, size_t *n_out) {
     const size_t n = (size_t) n_blocks;
     leaf_out.reserve((size_t) total * sizeof(la3dm_leaf), stream);
     k_leaf_fill<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
-        ab.as<float2>(), st.as<unsigned char>(), keys.as<long long>(), block_order.as<unsigned int>(), (unsigned int) n,
-        d_params, d_lut, nodes_pad, leaf_off.as<unsigned int>(), leaf_out.as<la3dm_leaf>());
+        pool.as<unsigned char>(), keys.as<long long>(), block_order.as<unsigned int>(), (unsigned int) n, d_params,
+        d_lut, leaf_off.as<unsigned int>(), leaf_out.as<la3dm_leaf>());
     LA3DM_CUDA(cudaMemcpyAsync(out, leaf_out.p, (size_t) total * sizeof(la3dm_leaf), cudaMemcpyDeviceToHost, stream));
     LA3DM_CUDA(cudaStreamSynchronize(stream));
 }

@@ -10,8 +10,9 @@ struct NeighbourPlan {
     unsigned int start[7];
     unsigned int count[7];
     unsigned int slot;      // block slot in the pool
-    unsigned int is_new;    // created this scan: nodes still hold garbage, kernel writes defaults
+    unsigned int is_new;    // created this scan: the record still holds garbage, the predict kernel writes defaults
 };
+static_assert(sizeof(NeighbourPlan) == 64, "NeighbourPlan is loaded as four 16-byte words");
 
 struct Map {
     // ---- configuration
@@ -26,67 +27,77 @@ struct Map {
     int num_sms = 148;
     std::string last_error;
 
-    // ---- persistent block pool (HBM-resident map)
-    //   d_keys[slot]                   BlockHashKey
-    //   d_ab  [slot * nodes + node]    float2 (m_A, m_B) | GP (m_ivar, ivar)
-    //   d_st  [slot * nodes_pad + node] uint8: bits 0..2 state, bit 7 classified
+    // ---- persistent block pool (HBM-resident map).  One record per block, hp.rec_bytes bytes (a multiple of 16):
+    //   float2 (m_A, m_B) | GP (m_ivar, ivar)  x nodes          at byte 0
+    //   uint8  state (bits 0..2) | classified (bit 7)  x nodes  at byte hp.st_off
+    // so that a block is one contiguous, 16-byte aligned span that a warp moves with 16-byte accesses.
     size_t pool_cap = 0;            // blocks
-    int nodes_pad = 0;
-    DevBuf keys, ab, st;
-    long long n_blocks = 0;         // host mirror of *d_nblocks
-    unsigned int *d_nblocks = nullptr;
+    DevBuf keys, pool;
+    long long n_blocks = 0;
     // open-addressing hash: key -> slot
     size_t hash_cap = 0;            // power of two
     DevBuf hkeys, hvals;
 
-    // ---- per-scan workspace
+    // ---- per-scan workspace, sized by `caps`
+    Caps caps{};                    // logical capacities the scan kernels check against
+    Caps alloc{};                   // what the buffers can hold (>= caps)
     DevBuf cloud;                   // uploaded scan (host entry point)
-    DevBuf sort_keys[2], sort_vals[2], flags, ranks, run_start, cub_tmp, scan64;
+    DevBuf sort_keys[2], sort_vals[2], run_start, cub_tmp, tiles, long_list, hit_cnt;
     DevBuf hits_ds;                 // float4 voxel-grid output of the cloud
     DevBuf frees_raw;               // float4 beam samples
     DevBuf xy;                      // float4 training set (x,y,z,label)
-    DevBuf mem_cnt, mem_off;        // memberships per entry
-    DevBuf pts_sorted;              // float4 block-sorted, pre-divided by ell
-    DevBuf db_id, db_start;         // data blocks: dense id, start (+ sentinel)
-    DevBuf cand[2], test_id, plan, miss;
-    DevBuf shard_ids;
-    unsigned int *d_mm = nullptr;   // [2][6] flipped min/max
+    DevBuf pts_sorted;              // float4 block-sorted, pre-scaled for the method's kernel
+    DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
+    DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
+    DevBuf test_id, plan;
+    size_t cub_tmp_bytes = 0;
+    unsigned int *d_mm = nullptr;   // [3][6] flipped min/max
     GridDesc *d_grid = nullptr;
     ScanCounters *d_cnt = nullptr;
     ScanCounters *h_cnt = nullptr;  // pinned
+    ScanArgs *d_args = nullptr;
+    ScanArgs *h_args = nullptr;     // pinned
     la3dm_scan_stats stats{};
-    int launches = 0;
+    int launches = 0;               // kernels enqueued by the last enqueue_scan()
     long long d2h_bytes = 0, h2d_bytes = 0;
+
+    // ---- whole-scan CUDA graph (re-captured when capacities or buffers change)
+    cudaGraphExec_t graph_exec = nullptr;
+    Caps graph_caps{};
+    int graph_frontend_only = -1;
+    int graph_launches = 0;
+    bool use_graph = true;
+    int replays = 0;                // scans re-run after a capacity overflow (lifetime counter)
 
     // ---- sharding (multi-GPU)
     int shard_rank = 0, shard_world = 1;
     unsigned int last_T = 0;        // test blocks of the last scan
 
     // ---- leaf export scratch
-    DevBuf leaf_cnt, leaf_off, leaf_out, export_buf, order_keys[2], order_vals[2], block_order;
+    DevBuf leaf_cnt, leaf_off, leaf_out, export_buf, export_tmp, order_keys[2], order_vals[2], block_order;
 
     Map() = default;
     ~Map();
 
     void init(int method, const la3dm_params &p, int device);
     void ensure_pool(size_t blocks);
+    void ensure_workspace();
+    void invalidate_graph();
     void insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
                        float max_range, bool frontend_only);
-    // phases
-    void frontend_bgk(const float *d_xyz, unsigned int n, int stride_f, float3 origin, float ds, float fr,
-                      float max_range);
-    unsigned int voxel_grid(const float *d_in, int stride_f, unsigned int n, float leaf, float4 *d_out,
-                            const unsigned int *d_out_off, float label, unsigned int *d_count, int which);
-    void minmax_points(const float *d_in, int stride_f, unsigned int n_host, const unsigned int *d_n,
-                       unsigned int *mm, unsigned int n_upper);
-    void bin_and_plan();
-    void predict();
-    void read_counters();
+    // the scan, enqueued on `stream` without host synchronisation (graph-capturable)
+    void enqueue_scan(bool frontend_only);
+    void enqueue_frontend_bgk();
+    void enqueue_voxel_grid(int which);
+    void enqueue_binning();
+    void enqueue_predict();
     // export
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();
     void export_leaves(la3dm_leaf *out, size_t cap, size_t *n);
     void sorted_block_order(DevBuf &order, size_t n);
+
+    unsigned char *record(size_t slot) const { return pool.as<unsigned char>() + slot * (size_t) hp.rec_bytes; }
 };
 
 }  // namespace la3dm_b200

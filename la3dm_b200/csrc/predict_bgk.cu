@@ -5,15 +5,21 @@
 //   Occupancy::update / get_var / get_prob (src/bgkoctomap/bgkoctree_node.cpp:27-44, bgkoctree_node.h:60),
 //   OcTree::is_leaf / prune (src/bgkoctomap/bgkoctree.cpp:72-82, 101-148), Block::get_loc (bgkblock.h:64-66).
 //
-// Mapping: one warp per test block (persistent grid, warps stride over the test-block list).  A lane owns the finest
-// octree slots lane, lane+32, ...; a slot whose ancestors were pruned resolves to the coarser leaf, handled by the
-// lane that owns the leaf's first descendant.  For each of the 7 neighbour blocks in ExtendedBlock order the warp
-// stages the neighbour's training points (float4: x/ell, y/ell, z/ell, label) through shared memory in 32-point tiles
-// and every lane accumulates (ybar, kbar) for its leaves sequentially in training-array order -- the same order of
-// fp32 additions as the CPU oracle -- then applies one Occupancy::update per neighbour with kbar > 0.
-// Results go back as coalesced float2 (alpha, beta) + state bytes; pruning runs in the same warp afterwards.
+// k_predict_bgk (block_depth <= 3, i.e. <= 64 finest voxels per block): one warp per test block, persistent grid.
+//   * the block's record (alpha/beta + state bytes, one contiguous 16-byte aligned span) is staged in shared memory
+//     with 16-byte accesses, updated and pruned there, and written back the same way;
+//   * a lane owns the finest octree slots lane and lane + 32; a slot whose ancestors were pruned resolves to the
+//     coarser leaf, handled by the lane that owns the leaf's first finest descendant;
+//   * the training points of the 7 neighbour blocks (ExtendedBlock order) are streamed as ONE sequence in tiles of 32
+//     through shared memory; points that cannot reach the slot's hull are culled per tile (warp-uniform);
+//   * the compact-support test (d < 1) runs per (point, leaf) in registers; pairs inside the support are appended to a
+//     per-warp queue, the kernel function (sqrt, sin, cos) is then evaluated DENSELY over the queue -- all 32 lanes
+//     busy instead of the few lanes that are in range -- and a third pass adds the values to each leaf's (ybar, kbar)
+//     in training-array order, i.e. the same order of fp32 additions as the CPU oracle;
+//   * one Occupancy::update per neighbour with kbar > 0, in ExtendedBlock order.
+// k_predict_bgk_deep (block_depth 4): previous formulation, 16 slots per lane, works on the record in global memory.
 //
-// Bound: FP32/SFU pipe (~24 flop per pair vs 17 B per voxel visit).
+// Bound: issue slots / FP32 pipe (~24 flop per pair vs 17 B per voxel visit).
 #include "engine.cuh"
 
 namespace la3dm_b200 {
@@ -21,13 +27,11 @@ namespace la3dm_b200 {
 namespace {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kTile = 32;
+constexpr int kPtTile = 32;
+constexpr int kQCap = 384;            // queue entries per warp; flushed when fewer than 64 are free
+constexpr int kRecMax = 672;          // bytes of a depth-3 record: 73 * 8 + 73 -> 16-byte multiple
 
-struct LeafRef {
-    int node;     // index into the block's node array (layer_off[d] + index); -1: slot not owned by this lane
-};
-
-// covSparse element (bgkinference.h:115-116), d already scaled by 1/ell; caller guarantees d < 1
+// covSparse element (bgkinference.h:115-116), d already scaled by 1/ell; caller guarantees d <= 1
 __device__ __forceinline__ float sparse_kernel(float d, float sf2) {
     const float t = d * 2.0f * 3.1415926f;
     float s, c;
@@ -36,8 +40,12 @@ __device__ __forceinline__ float sparse_kernel(float d, float sf2) {
     return k < 0.0f ? 0.0f : k;      // bgkinference.h:120-125
 }
 
+struct UpdateParams {
+    float var_thresh, occupied_thresh, free_thresh;
+};
+
 // Occupancy::update (bgkoctree_node.cpp:31-44); returns the new state
-__device__ __forceinline__ unsigned char bgk_update(float &a, float &b, float ybar, float kbar, const DevParams &P) {
+__device__ __forceinline__ unsigned char bgk_update(float &a, float &b, float ybar, float kbar, const UpdateParams &P) {
     a += ybar;
     b += kbar - ybar;
     const float var = (a * b) / ((a + b) * (a + b) * (a + b + 1.0f));
@@ -46,95 +54,371 @@ __device__ __forceinline__ unsigned char bgk_update(float &a, float &b, float yb
     return p > P.occupied_thresh ? LA3DM_OCCUPIED : (p < P.free_thresh ? LA3DM_FREE : LA3DM_UNKNOWN);
 }
 
-template <int kSlotsPerLane>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_predict_bgk(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__ d_t,
-              const float4 *__restrict__ pts, const long long *__restrict__ keys, float2 *__restrict__ ab,
-              unsigned char *__restrict__ st, const float3 *__restrict__ lut, const DevParams *__restrict__ Pg,
-              int nodes_pad, int shard_rank, int shard_world, ScanCounters *cnt) {
-    __shared__ float4 tile[kWarpsPerCta][kTile];
-    __shared__ DevParams Ps;
-    if (threadIdx.x < sizeof(DevParams) / 4) reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
-    __syncthreads();
-    const DevParams &P = Ps;
+struct WarpSmem {
+    uint4 rec[kRecMax / 16];          // the block record
+    float4 pts[kPtTile];                // current tile of training points (x/ell, y/ell, z/ell, label)
+    float q[kQCap];                   // queue: squared distances in, kernel values out
+    unsigned int masks[kPtTile][2];     // lanes inside the support, per (point of the tile, slot)
+};
 
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
+              const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
+              const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt) {
+    __shared__ WarpSmem sm[kWarpsPerCta];
+    __shared__ DevParams Ps;
+    if (threadIdx.x < sizeof(DevParams) / 4)
+        reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    __syncthreads();
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int T = *d_t;
+    const unsigned int lt = (1u << lane) - 1u;
+    WarpSmem &S = sm[warp];
+    const unsigned int T = cnt->n_test_blocks;
     const unsigned int warps_total = gridDim.x * kWarpsPerCta;
-    const int D = P.depth, finest_off = P.layer_off[D - 1], finest = P.finest;
-    const float ell = P.ell, sf2 = P.sf2;
+    const int D = P.depth, finest = P.finest, nodes = P.nodes, st_off = P.st_off;
+    const int rec_words = P.rec_bytes >> 4;
+    const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
+    const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
+    const int shard_world = A->shard_world, shard_rank = A->shard_rank;
+    float2 *rab = reinterpret_cast<float2 *>(S.rec);
+    unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + st_off;
+
+    // hull of the leaf centres of a slot, relative to the block centre, in units of ell (conservative): every leaf
+    // centre lies within (block_size - resolution) / 2 of the block centre; with 64 finest voxels slot 0 / 1 hold the
+    // lower / upper half in x (bit 5 of the finest index is the x bit of the depth-1 child, bgkblock.cpp:23-27)
+    const float reach = 0.5f * (bs - P.resolution) * 1.001f / ell;
+    float hx_lo[2], hx_hi[2];
+    hx_lo[0] = -reach; hx_hi[0] = finest > 32 ? 1e-3f * reach : reach;
+    hx_lo[1] = finest > 32 ? 0.0f : -reach; hx_hi[1] = reach;
+    const float cull2 = 1.0f + 1e-4f;
 
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
     for (unsigned int t = blockIdx.x * kWarpsPerCta + warp; t < T; t += warps_total) {
         if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
-        const NeighbourPlan pl = plan[t];
-        const size_t slot = pl.slot;
-        float2 *bab = ab + slot * (size_t) P.nodes;
-        unsigned char *bst = st + slot * (size_t) nodes_pad;
-
-        if (pl.is_new) {   // fresh Block: every node = (prior_A, prior_B, UNKNOWN, !classified) (bgkoctree_node.h:34)
-            for (int n = lane; n < P.nodes; n += 32) { bab[n] = make_float2(P.def_a, P.def_b); bst[n] = LA3DM_UNKNOWN; }
-            __syncwarp();
+        // ---- plan: lanes 0..6 hold start/count of one neighbour each
+        const NeighbourPlan *pl = plan + t;
+        const unsigned int slot = pl->slot, is_new = pl->is_new;
+        const unsigned int my_start = lane < 7 ? pl->start[lane] : 0u, my_count = lane < 7 ? pl->count[lane] : 0u;
+        unsigned int pre = my_count;                        // inclusive prefix over lanes 0..6
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += up;
+        }
+        const unsigned int tot = __shfl_sync(0xffffffffu, pre, 6);
+        pre -= my_count;                                    // exclusive
+        // ---- record -> shared memory
+        uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) slot * (size_t) P.rec_bytes);
+        __syncwarp();
+        if (is_new) {   // fresh Block: every node = (prior_A, prior_B, UNKNOWN, !classified) (bgkoctree_node.h:34)
+            for (int n = lane; n < nodes; n += 32) { rab[n] = make_float2(P.def_a, P.def_b); rst[n] = LA3DM_UNKNOWN; }
+            for (int n = st_off + nodes + lane; n < P.rec_bytes; n += 32) reinterpret_cast<unsigned char *>(S.rec)[n] = 0;
+        } else {
+            for (int w = lane; w < rec_words; w += 32) S.rec[w] = grec[w];
         }
         // block centre from its key (hash_key_to_block, bgkblock.cpp:79-83)
         const long long key = keys[slot];
+        const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
+                    cz = axis_center(key & 0xFFFFF, bs);
+        const float ccx = cx / ell, ccy = cy / ell, ccz = cz / ell;
+        __syncwarp();
+
+        // ---- resolve this lane's leaves
+        int node[2];
+        float px[2], py[2], pz[2], a[2], b[2], yb[2], kb[2];
+        unsigned char state[2], touched[2];
+        int owned = 0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int j = lane + 32 * s;
+            node[s] = -1;
+            touched[s] = 0;
+            state[s] = LA3DM_UNKNOWN;
+            a[s] = b[s] = px[s] = py[s] = pz[s] = 0.f;
+            yb[s] = kb[s] = 0.f;
+            if (j < finest) {
+                // walk up while PRUNED: leaf (d, i) is owned by the lane of its first finest descendant
+                int d = D - 1, i = j, shift = 0;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == kStPRUNED) { --d; i >>= 3; shift += 3; }
+                const unsigned char sb = rst[P.layer_off[d] + i];
+                if (((i << shift) == j) && ((sb & 7) != kStPRUNED)) {
+                    const int n = P.layer_off[d] + i;
+                    node[s] = n;
+                    state[s] = sb;
+                    const float2 v = rab[n];
+                    a[s] = v.x; b[s] = v.y;
+                    const float3 off = lut[n];
+                    // Block::get_loc: LUT offset + centre, then covSparse's  xs / ell
+                    px[s] = (off.x + cx) / ell; py[s] = (off.y + cy) / ell; pz[s] = (off.z + cz) / ell;
+                    ++owned;
+                }
+            }
+        }
+        visits += owned;
+        pairs += (unsigned long long) owned * tot;
+        const unsigned int have0 = __ballot_sync(0xffffffffu, node[0] >= 0);
+        const unsigned int have1 = __ballot_sync(0xffffffffu, node[1] >= 0);
+
+        // ---- stream the neighbours' points
+        bool open = false;      // a neighbour's sums are being accumulated
+        for (unsigned int base = 0; base < tot; base += kPtTile) {
+            const unsigned int gi = base + lane;
+            const bool valid = gi < tot;
+            // which neighbour range holds global point gi (ranges are concatenated in ExtendedBlock order)
+            int nb = 0;
+#pragma unroll
+            for (int k = 1; k < 7; ++k) nb += (gi >= __shfl_sync(0xffffffffu, pre, k)) ? 1 : 0;
+            const unsigned int nb_start = __shfl_sync(0xffffffffu, my_start, nb);
+            const unsigned int nb_pre = __shfl_sync(0xffffffffu, pre, nb);
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) z = pts[nb_start + (gi - nb_pre)];
+            // first point of a neighbour's range: the previous neighbour's sums are complete
+            const unsigned int bnd = __ballot_sync(0xffffffffu, valid && gi == nb_pre);
+            // cull against the slot hulls
+            bool keep0 = false, keep1 = false;
+            if (valid) {
+                const float ry = fmaxf(fabsf(z.y - ccy) - reach, 0.f), rz = fmaxf(fabsf(z.z - ccz) - reach, 0.f);
+                const float ryz = ry * ry + rz * rz;
+                const float dxc = z.x - ccx;
+                const float r0 = fmaxf(fmaxf(hx_lo[0] - dxc, dxc - hx_hi[0]), 0.f);
+                const float r1 = fmaxf(fmaxf(hx_lo[1] - dxc, dxc - hx_hi[1]), 0.f);
+                keep0 = (r0 * r0 + ryz) < cull2;
+                keep1 = (r1 * r1 + ryz) < cull2;
+            }
+            const unsigned int m0 = __ballot_sync(0xffffffffu, keep0) & (have0 ? 0xffffffffu : 0u);
+            const unsigned int m1 = __ballot_sync(0xffffffffu, keep1) & (have1 ? 0xffffffffu : 0u);
+            __syncwarp();
+            S.pts[lane] = z;
+            __syncwarp();
+
+            unsigned int todo = valid ? 0u : 0u;
+            todo = __ballot_sync(0xffffffffu, valid);       // every valid point is walked (boundaries live on them)
+            unsigned int batch = 0, nq = 0;
+            while (true) {
+                // ---- pass 1: support test, queue the squared distances
+                while (todo && nq <= (unsigned int) (kQCap - 64)) {
+                    const int q = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    batch |= 1u << q;
+                    const unsigned int t0 = (m0 >> q) & 1u, t1 = (m1 >> q) & 1u;
+                    if (!(t0 | t1)) continue;
+                    const float4 zq = S.pts[q];
+                    if (t0) {
+                        const float dx = zq.x - px[0], dy = zq.y - py[0], dz = zq.z - pz[0];
+                        const float d2 = dx * dx + (dy * dy + dz * dz);    // Eigen rowwise().norm() of a 3-vector, squared
+                        const bool in = node[0] >= 0 && d2 < 1.0f;        // k <= 0 for d >= 1 (clamped upstream)
+                        const unsigned int mk = __ballot_sync(0xffffffffu, in);
+                        if (in) S.q[nq + __popc(mk & lt)] = d2;
+                        if (lane == 0) S.masks[q][0] = mk;
+                        nq += __popc(mk);
+                    }
+                    if (t1) {
+                        const float dx = zq.x - px[1], dy = zq.y - py[1], dz = zq.z - pz[1];
+                        const float d2 = dx * dx + (dy * dy + dz * dz);
+                        const bool in = node[1] >= 0 && d2 < 1.0f;
+                        const unsigned int mk = __ballot_sync(0xffffffffu, in);
+                        if (in) S.q[nq + __popc(mk & lt)] = d2;
+                        if (lane == 0) S.masks[q][1] = mk;
+                        nq += __popc(mk);
+                    }
+                }
+                __syncwarp();
+                // ---- pass 2: the kernel function, densely over the queue
+                for (unsigned int i = lane; i < nq; i += 32) S.q[i] = sparse_kernel(sqrtf(S.q[i]), sf2);
+                __syncwarp();
+                // ---- pass 3: add to the leaves in training order; neighbour boundaries trigger Occupancy::update
+                unsigned int qb = 0;
+                while (batch) {
+                    const int q = __ffs(batch) - 1;
+                    batch &= batch - 1;
+                    if ((bnd >> q) & 1u) {
+                        if (open) {
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+                                if (node[s] >= 0 && kb[s] > 0.0f) {                      // bgkoctomap.cpp:332
+                                    state[s] = bgk_update(a[s], b[s], yb[s], kb[s], U) | 0x80;   // classified = true
+                                    touched[s] = 1;
+                                }
+                                yb[s] = kb[s] = 0.f;
+                            }
+                        }
+                        open = true;
+                    }
+                    const unsigned int t0 = (m0 >> q) & 1u, t1 = (m1 >> q) & 1u;
+                    if (!(t0 | t1)) continue;
+                    const float w = S.pts[q].w;
+                    if (t0) {
+                        const unsigned int mk = S.masks[q][0];
+                        if ((mk >> lane) & 1u) {
+                            const float k = S.q[qb + __popc(mk & lt)];
+                            yb[0] += k * w;
+                            kb[0] += k;
+                        }
+                        qb += __popc(mk);
+                    }
+                    if (t1) {
+                        const unsigned int mk = S.masks[q][1];
+                        if ((mk >> lane) & 1u) {
+                            const float k = S.q[qb + __popc(mk & lt)];
+                            yb[1] += k * w;
+                            kb[1] += k;
+                        }
+                        qb += __popc(mk);
+                    }
+                }
+                if (!todo) break;
+                nq = 0;
+                __syncwarp();
+            }
+        }
+        if (open) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (node[s] >= 0 && kb[s] > 0.0f) {
+                    state[s] = bgk_update(a[s], b[s], yb[s], kb[s], U) | 0x80;
+                    touched[s] = 1;
+                }
+        }
+
+        // ---- write back into the staged record
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (node[s] >= 0 && touched[s]) {
+                rab[node[s]] = make_float2(a[s], b[s]);
+                rst[node[s]] = state[s];
+                ++updates;
+                any = true;
+            }
+        }
+        const bool dirty = __any_sync(0xffffffffu, any) || is_new;
+        __syncwarp();
+        if (dirty) {
+            // OcTree::prune (bgkoctree.cpp:101-148): deepest layer first; 8 equal FREE/OCCUPIED siblings collapse into
+            // the parent (copy of child 0's m_A, m_B, state -- `classified` is not copied, bgkoctree_node.h:40-45)
+            for (int d = D - 1; d > 0; --d) {
+                const int off = P.layer_off[d], poff = P.layer_off[d - 1];
+                const int groups = 1 << (3 * (d - 1));
+                for (int g = lane; g < groups; g += 32) {
+                    const unsigned char s0 = rst[off + 8 * g] & 7;
+                    if (s0 == LA3DM_FREE || s0 == LA3DM_OCCUPIED) {
+                        bool same = true;
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) same = same && ((rst[off + 8 * g + i] & 7) == s0);
+                        if (same) {
+                            rab[poff + g] = rab[off + 8 * g];
+                            rst[poff + g] = (rst[poff + g] & 0x80) | s0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) rst[off + 8 * g + i] = (rst[off + 8 * g + i] & 0x80) | kStPRUNED;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            for (int w = lane; w < rec_words; w += 32) grec[w] = S.rec[w];
+        }
+    }
+
+    // stats: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        visits += __shfl_xor_sync(0xffffffffu, visits, o);
+        updates += __shfl_xor_sync(0xffffffffu, updates, o);
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    }
+    if (lane == 0 && visits) {
+        atomicAdd(&cnt->visits, visits);
+        atomicAdd(&cnt->updates, updates);
+        atomicAdd(&cnt->pairs, pairs);
+    }
+}
+
+// ---- block_depth 4: 512 finest voxels per block, 16 slots per lane, record updated in global memory ----------------
+constexpr int kDeepSlots = 16;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
+                   const long long *__restrict__ keys, unsigned char *__restrict__ pool,
+                   const float3 *__restrict__ lut, const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A,
+                   ScanCounters *cnt) {
+    __shared__ float4 tile[kWarpsPerCta][kPtTile];
+    __shared__ DevParams Ps;
+    if (threadIdx.x < sizeof(DevParams) / 4)
+        reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    __syncthreads();
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int T = cnt->n_test_blocks;
+    const unsigned int warps_total = gridDim.x * kWarpsPerCta;
+    const int D = P.depth, finest = P.finest;
+    const float ell = P.ell, sf2 = P.sf2;
+    const int shard_world = A->shard_world, shard_rank = A->shard_rank;
+    unsigned long long visits = 0, updates = 0, pairs = 0;
+
+    for (unsigned int t = blockIdx.x * kWarpsPerCta + warp; t < T; t += warps_total) {
+        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+        const NeighbourPlan pl = plan[t];
+        unsigned char *rec = pool + (size_t) pl.slot * (size_t) P.rec_bytes;
+        float2 *bab = reinterpret_cast<float2 *>(rec);
+        unsigned char *bst = rec + P.st_off;
+        if (pl.is_new) {
+            for (int n = lane; n < P.nodes; n += 32) { bab[n] = make_float2(P.def_a, P.def_b); bst[n] = LA3DM_UNKNOWN; }
+            __syncwarp();
+        }
+        const long long key = keys[pl.slot];
         const float cx = axis_center(key >> 40, P.block_size), cy = axis_center((key >> 20) & 0xFFFFF, P.block_size),
                     cz = axis_center(key & 0xFFFFF, P.block_size);
-
-        // resolve this lane's leaves
-        int node[kSlotsPerLane];
-        float px[kSlotsPerLane], py[kSlotsPerLane], pz[kSlotsPerLane], a[kSlotsPerLane], b[kSlotsPerLane];
-        unsigned char state[kSlotsPerLane], touched[kSlotsPerLane];
+        int node[kDeepSlots];
+        float px[kDeepSlots], py[kDeepSlots], pz[kDeepSlots], a[kDeepSlots], b[kDeepSlots];
+        unsigned char state[kDeepSlots], touched[kDeepSlots];
 #pragma unroll
-        for (int s = 0; s < kSlotsPerLane; ++s) {
+        for (int s = 0; s < kDeepSlots; ++s) {
             const int j = lane + 32 * s;
             node[s] = -1;
             touched[s] = 0;
             state[s] = LA3DM_UNKNOWN;
             a[s] = b[s] = px[s] = py[s] = pz[s] = 0.f;
             if (j < finest) {
-                // walk up while PRUNED: leaf (d, i) is owned by the lane of its first finest descendant
                 int d = D - 1, i = j, shift = 0;
                 while (d > 0 && (bst[P.layer_off[d] + i] & 7) == kStPRUNED) { --d; i >>= 3; shift += 3; }
                 const unsigned char sb = bst[P.layer_off[d] + i];
-                const bool owner = ((i << shift) == j) && ((sb & 7) != kStPRUNED);
-                if (owner) {
+                if (((i << shift) == j) && ((sb & 7) != kStPRUNED)) {
                     const int n = P.layer_off[d] + i;
                     node[s] = n;
                     state[s] = sb;
                     const float2 v = bab[n];
                     a[s] = v.x; b[s] = v.y;
                     const float3 off = lut[n];
-                    // Block::get_loc: LUT offset + centre, then covSparse's  xs / ell
                     px[s] = (off.x + cx) / ell; py[s] = (off.y + cy) / ell; pz[s] = (off.z + cz) / ell;
                     ++visits;
                 }
             }
         }
-
-        // 7 neighbours in ExtendedBlock order, one Occupancy::update each (bgkoctomap.cpp:314-335)
         for (int nb = 0; nb < 7; ++nb) {
             const unsigned int cntp = pl.count[nb];
             if (cntp == 0) continue;
             const float4 *src = pts + pl.start[nb];
-            float yb[kSlotsPerLane], kb[kSlotsPerLane];
+            float yb[kDeepSlots], kb[kDeepSlots];
 #pragma unroll
-            for (int s = 0; s < kSlotsPerLane; ++s) { yb[s] = 0.f; kb[s] = 0.f; }
-            for (unsigned int base = 0; base < cntp; base += kTile) {
-                const unsigned int m = min((unsigned int) kTile, cntp - base);
+            for (int s = 0; s < kDeepSlots; ++s) { yb[s] = 0.f; kb[s] = 0.f; }
+            for (unsigned int base = 0; base < cntp; base += kPtTile) {
+                const unsigned int m = min((unsigned int) kPtTile, cntp - base);
                 __syncwarp();
                 if ((unsigned int) lane < m) tile[warp][lane] = src[base + lane];
                 __syncwarp();
                 for (unsigned int q = 0; q < m; ++q) {
                     const float4 z = tile[warp][q];
 #pragma unroll
-                    for (int s = 0; s < kSlotsPerLane; ++s) {
+                    for (int s = 0; s < kDeepSlots; ++s) {
                         if (node[s] < 0) continue;
                         const float dx = z.x - px[s], dy = z.y - py[s], dz = z.z - pz[s];
-                        const float d = sqrtf(dx * dx + (dy * dy + dz * dz));   // Eigen rowwise().norm() of a 3-vector
-                        if (d < 1.0f) {                                          // k <= 0 for d >= 1 (clamped upstream)
-                            const float k = sparse_kernel(d, sf2);
+                        const float d2 = dx * dx + (dy * dy + dz * dz);
+                        if (d2 < 1.0f) {
+                            const float k = sparse_kernel(sqrtf(d2), sf2);
                             yb[s] += k * z.w;
                             kb[s] += k;
                         }
@@ -142,20 +426,18 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const unsigned int *__rest
                 }
             }
 #pragma unroll
-            for (int s = 0; s < kSlotsPerLane; ++s) {
+            for (int s = 0; s < kDeepSlots; ++s) {
                 if (node[s] >= 0) {
                     pairs += cntp;
-                    if (kb[s] > 0.0f) {                                          // bgkoctomap.cpp:332
-                        state[s] = bgk_update(a[s], b[s], yb[s], kb[s], P) | 0x80;   // classified = true
+                    if (kb[s] > 0.0f) {
+                        state[s] = bgk_update(a[s], b[s], yb[s], kb[s], U) | 0x80;
                         touched[s] = 1;
                     }
                 }
             }
         }
-
-        // write back
 #pragma unroll
-        for (int s = 0; s < kSlotsPerLane; ++s) {
+        for (int s = 0; s < kDeepSlots; ++s) {
             if (node[s] >= 0 && touched[s]) {
                 bab[node[s]] = make_float2(a[s], b[s]);
                 bst[node[s]] = state[s];
@@ -163,9 +445,6 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const unsigned int *__rest
             }
         }
         __syncwarp();
-
-        // OcTree::prune (bgkoctree.cpp:101-148): deepest layer first; 8 equal FREE/OCCUPIED siblings collapse into the
-        // parent (copy of child 0's m_A, m_B, state -- `classified` is not copied, bgkoctree_node.h:40-45)
         for (int d = D - 1; d > 0; --d) {
             const int off = P.layer_off[d], poff = P.layer_off[d - 1];
             const int groups = 1 << (3 * (d - 1));
@@ -186,8 +465,6 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const unsigned int *__rest
             __syncwarp();
         }
     }
-
-    // stats: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
         visits += __shfl_xor_sync(0xffffffffu, visits, o);
         updates += __shfl_xor_sync(0xffffffffu, updates, o);
@@ -200,25 +477,28 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const unsigned int *__rest
     }
 }
 
+__global__ void k_scan_end(ScanCounters *c, const ScanArgs *__restrict__ A) {
+    c->n_blocks = A->n_blocks + (c->overflow ? 0u : c->n_new_blocks);
+}
+
 }  // namespace
 
-void Map::predict() {
-    if (last_T == 0) return;
+void Map::enqueue_predict() {
     if (hp.method != LA3DM_BGK) throw StatusError{LA3DM_ERR_UNSUPPORTED, "predict: method not implemented yet"};
     const int ctas = num_sms * 4;
-    const int slots = (hp.finest + 31) / 32;
-    LA3DM_CUDA(cudaEventRecord(ev_p0, stream));
-#define LAUNCH(S)                                                                                              \
-    k_predict_bgk<S><<<ctas, kWarpsPerCta * 32, 0, stream>>>(                                                  \
-        plan.as<NeighbourPlan>(), &d_cnt->n_test_blocks, pts_sorted.as<float4>(), keys.as<long long>(),        \
-        ab.as<float2>(), st.as<unsigned char>(), d_lut, d_params, nodes_pad, shard_rank, shard_world, d_cnt)
-    if (slots <= 1) LAUNCH(1);
-    else if (slots <= 2) LAUNCH(2);
-    else if (slots <= 16) LAUNCH(16);
+    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    if (hp.depth <= 3)
+        k_predict_bgk<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
+                                                              keys.as<long long>(), pool.as<unsigned char>(), d_lut,
+                                                              d_params, d_args, d_cnt);
+    else if (hp.depth == 4)
+        k_predict_bgk_deep<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
+                                                                   keys.as<long long>(), pool.as<unsigned char>(),
+                                                                   d_lut, d_params, d_args, d_cnt);
     else throw StatusError{LA3DM_ERR_UNSUPPORTED, "block_depth > 4 not supported by the BGK kernel yet"};
-#undef LAUNCH
-    LA3DM_CUDA(cudaEventRecord(ev_p1, stream));
-    ++launches;
+    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    k_scan_end<<<1, 1, 0, stream>>>(d_cnt, d_args);
+    launches += 2;
 }
 
 }  // namespace la3dm_b200

@@ -1,19 +1,18 @@
 // la3dm_b200 -- multi-GPU exchange of updated block states.
 //
 // Test blocks of a scan are dealt round-robin over ranks (t % world == rank) inside the fused predict kernel; every
-// rank runs the front-end and the binning redundantly, so all ranks agree on the test-block list, the slots and the
-// neighbour plan.  After the scan each rank packs the full node arrays of ITS test blocks into fixed-size rows; the
-// caller all-gathers the rows over NCCL/NVLink and every rank scatters the peers' rows into its replica.
+// rank runs the front-end and the binning redundantly, so all ranks agree on the test-block list and the neighbour
+// plan.  After the scan each rank packs the records of ITS test blocks into fixed-size rows; the caller all-gathers
+// the rows over NCCL/NVLink and every rank scatters the peers' rows into its replica.
 #include "engine.cuh"
 
 namespace la3dm_b200 {
 namespace {
 
-// row = nodes * float2 (alpha, beta) followed by nodes_pad state bytes; nodes_pad is a multiple of 16 so rows stay
-// 8-byte aligned
+// row = one block record (hp.rec_bytes, a multiple of 16): (alpha, beta) pairs followed by the state bytes
 __global__ void k_shard_copy(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__ d_t,
-                             float2 *ab, unsigned char *st, int nodes, int nodes_pad, unsigned char *rows,
-                             unsigned int rows_per_rank, int world, int my_rank, int pack) {
+                             unsigned char *pool, int rec_bytes, unsigned char *rows, unsigned int rows_per_rank,
+                             int world, int my_rank, int pack) {
     const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const unsigned int total_rows = pack ? rows_per_rank : rows_per_rank * (unsigned int) world;
     if (w >= total_rows) return;
@@ -22,20 +21,11 @@ __global__ void k_shard_copy(const NeighbourPlan *__restrict__ plan, const unsig
     if (!pack && (int) q == my_rank) return;
     const unsigned int t = r * (unsigned int) world + q;
     if (t >= *d_t) return;
-    const size_t row_bytes = (size_t) nodes * 8 + (size_t) nodes_pad;
-    unsigned char *row = rows + (size_t) w * row_bytes;
-    const size_t slot = plan[t].slot;
-    float2 *bab = ab + slot * (size_t) nodes;
-    unsigned char *bst = st + slot * (size_t) nodes_pad;
-    float2 *rab = reinterpret_cast<float2 *>(row);
-    unsigned char *rst = row + (size_t) nodes * 8;
-    if (pack) {
-        for (int i = lane; i < nodes; i += 32) rab[i] = bab[i];
-        for (int i = lane; i < nodes_pad; i += 32) rst[i] = i < nodes ? bst[i] : 0;
-    } else {
-        for (int i = lane; i < nodes; i += 32) bab[i] = rab[i];
-        for (int i = lane; i < nodes; i += 32) bst[i] = rst[i];
-    }
+    uint4 *row = reinterpret_cast<uint4 *>(rows + (size_t) w * rec_bytes);
+    uint4 *rec = reinterpret_cast<uint4 *>(pool + (size_t) plan[t].slot * rec_bytes);
+    const int words = rec_bytes >> 4;
+    if (pack) for (int i = lane; i < words; i += 32) row[i] = rec[i];
+    else for (int i = lane; i < words; i += 32) rec[i] = row[i];
 }
 
 }  // namespace
@@ -45,9 +35,7 @@ using la3dm_b200::Map;
 
 extern "C" {
 
-int64_t la3dm_shard_row_bytes(const la3dm_map *map) {
-    return map ? (int64_t) map->m.hp.nodes * 8 + map->m.nodes_pad : -1;
-}
+int64_t la3dm_shard_row_bytes(const la3dm_map *map) { return map ? (int64_t) map->m.hp.rec_bytes : -1; }
 
 int64_t la3dm_shard_rows(const la3dm_map *map) {
     if (!map) return -1;
@@ -63,9 +51,8 @@ static int shard_copy(la3dm_map *map, void *rows, int pack) {
     if (cudaSetDevice(m.device) != cudaSuccess) return LA3DM_ERR_CUDA;
     const unsigned int total = pack ? rpr : rpr * (unsigned int) m.shard_world;
     la3dm_b200::k_shard_copy<<<la3dm_b200::ceil_div((long long) total * 32, 256), 256, 0, m.stream>>>(
-        m.plan.as<la3dm_b200::NeighbourPlan>(), &m.d_cnt->n_test_blocks, m.ab.as<float2>(),
-        m.st.as<unsigned char>(), m.hp.nodes, m.nodes_pad, static_cast<unsigned char *>(rows), rpr, m.shard_world,
-        m.shard_rank, pack);
+        m.plan.as<la3dm_b200::NeighbourPlan>(), &m.d_cnt->n_test_blocks, m.pool.as<unsigned char>(), m.hp.rec_bytes,
+        static_cast<unsigned char *>(rows), rpr, m.shard_world, m.shard_rank, pack);
     if (cudaStreamSynchronize(m.stream) != cudaSuccess) {
         m.last_error = cudaGetErrorString(cudaGetLastError());
         return LA3DM_ERR_CUDA;
