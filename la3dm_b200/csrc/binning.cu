@@ -436,8 +436,7 @@ void Map::enqueue_binning() {
     unsigned int *tile_sums = tiles.as<unsigned int>();
 
     // bbox of the training set and the float-stepped block grid; dense per-cell tables start empty
-    const int mm_grid = std::max(1, std::min(ceil_div(caps.train, kThreads), num_sms * 4));
-    k_bbox_minmax<<<mm_grid, kThreads, 0, stream>>>(d_xy, d_cnt, mm);
+    // (the bounding box mm was accumulated by the front-end kernels that wrote xy)
     LA3DM_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(GridDesc), stream));
     LA3DM_CUDA(cudaMemsetAsync(cell_db.p, 0, (size_t) caps.cells * 4, stream));
     const unsigned int n_words = (caps.cells + 31) / 32;
@@ -462,7 +461,7 @@ void Map::enqueue_binning() {
                                                      pts_sorted.as<float4>(), db_id.as<unsigned int>(),
                                                      db_start.as<unsigned int>(), cell_db.as<unsigned int>(),
                                                      test_bits.as<unsigned int>());
-    launches += 9 + 2 + (end_bit + 7) / 8;
+    launches += 8 + 2 + (end_bit + 7) / 8;
 
     // test blocks, their slots in the map and their neighbour plans
     const int w_tiles = ceil_div(n_words, kThreads);

@@ -111,6 +111,8 @@ struct ScanArgs {
     int shard_rank, shard_world;
     unsigned int n_blocks;  // blocks in the map before this scan
     unsigned int pool_cap;  // block slots allocated
+    const float *beam_tab;  // beam_tab[e] = fr + fr + ... (e fp32 additions): distance of beam sample e
+    unsigned int beam_tab_n;
 };
 
 // per-scan block grid: restates get_blocks_in_bbox (src/bgkoctomap/bgkoctomap.cpp:486-495) as a Cartesian product of
@@ -161,7 +163,8 @@ struct ScanCounters {
     unsigned long long visits, updates, pairs;
     unsigned int n_leaves;
     unsigned int overflow;       // OVF_* bits
-    unsigned int n_long_runs[2]; // voxel-grid runs handed to the long-run kernel
+    unsigned int n_long_runs[2]; // voxel-grid runs handed to the long-run kernel, one CTA each
+    unsigned int n_mid_runs[2];  // ... one warp each
     unsigned int grid_irregular;
     unsigned int n_blocks;       // blocks in the map after the scan
     unsigned int vg_cells_needed;
@@ -171,8 +174,10 @@ struct ScanCounters {
 constexpr int kTile = 2048;          // elements per CTA in the two-kernel compactions (count per tile, then place)
 constexpr int kTileThreads = 256;
 constexpr int kTileItems = kTile / kTileThreads;
-constexpr int kMaxLongRuns = 4096;   // voxel-grid runs longer than kLongRun are summed by a whole CTA each
-constexpr int kLongRun = 48;
+constexpr int kLongRun = 2048;       // voxel-grid runs longer than this are summed by a whole CTA each
+constexpr int kMidRun = 48;          // ... longer than this by a warp each; shorter ones by one thread
+constexpr int kMaxLongRuns = 4096;
+constexpr int kMaxMidRuns = 32768;
 
 inline int ceil_div(long long a, int b) { return (int) ((a + b - 1) / b); }
 

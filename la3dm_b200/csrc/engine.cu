@@ -237,6 +237,22 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     LA3DM_CUDA(cudaStreamSynchronize(stream));
 }
 
+// beam_sample walks a beam with  d = fr; while (d < l) { ...; d += fr; }  in fp32 (src/bgkoctomap/bgkoctomap.cpp:451-455):
+// sample e sits at fr added to itself e times, whatever the hit.  The table restates that accumulation once per
+// free_resolution so that the kernels index it instead of re-running the dependent additions for every hit.
+constexpr unsigned int kBeamTab = 65536;
+
+void Map::ensure_beam_table(float fr) {
+    if (beam_tab.p && fr == beam_tab_fr) return;
+    std::vector<float> t(kBeamTab);
+    volatile float d = fr;
+    for (unsigned int i = 0; i < kBeamTab; ++i) { t[i] = d; d = d + fr; }
+    if (beam_tab.reserve(kBeamTab * sizeof(float), stream)) invalidate_graph();
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    LA3DM_CUDA(cudaMemcpy(beam_tab.p, t.data(), kBeamTab * sizeof(float), cudaMemcpyHostToDevice));
+    beam_tab_fr = fr;
+}
+
 void Map::invalidate_graph() {
     if (graph_exec) {
         cudaStreamSynchronize(stream);
@@ -255,8 +271,9 @@ void Map::ensure_workspace() {
         moved |= sort_vals[i].reserve(n_sort * 4, stream);
     }
     moved |= run_start.reserve((std::max<size_t>(caps.points, caps.raw) + 2) * 4, stream);
-    moved |= tiles.reserve((n_sort / kTile + (size_t) caps.cells / 32 / 256 + 16) * 8, stream);
-    moved |= long_list.reserve((size_t) 2 * kMaxLongRuns * 4, stream);
+    moved |= tiles.reserve((n_sort / kTile + (size_t) caps.points / 256 + (size_t) caps.cells / 32 / 256 + 16) * 8, stream);
+    moved |= long_list.reserve((size_t) 2 * (kMaxLongRuns + kMaxMidRuns) * 4, stream);
+    moved |= long_flags.reserve((std::max<size_t>(caps.points, caps.raw) / 256 + 2) * 13, stream);
     moved |= hit_cnt.reserve((size_t) caps.points * 4, stream);
     moved |= hits_ds.reserve((size_t) caps.points * sizeof(float4), stream);
     moved |= frees_raw.reserve((size_t) caps.raw * sizeof(float4), stream);
@@ -293,6 +310,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (n > caps.points) caps.points = grow_to((unsigned int) n, 4096);
         ensure_workspace();
         ensure_pool((size_t) n_blocks + caps.tests);
+        ensure_beam_table(fr);
 
         ScanArgs &a = *h_args;
         a.xyz = d_xyz; a.n = (unsigned int) n; a.stride_f = (int) (stride_bytes / 4);
@@ -302,6 +320,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.frontend_only = frontend_only ? 1 : 0;
         a.shard_rank = shard_rank; a.shard_world = shard_world;
         a.n_blocks = (unsigned int) n_blocks; a.pool_cap = (unsigned int) pool_cap;
+        a.beam_tab = beam_tab.as<float>(); a.beam_tab_n = kBeamTab;
 
         LA3DM_CUDA(cudaEventRecord(ev0, stream));
         LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));
@@ -340,7 +359,11 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         // a workspace was too small: nothing was written to the map; grow from the sizes the device reports and replay
         ++replays;
         if (ovf & OVF_EXTENT) throw StatusError{LA3DM_ERR_EXTENT, "scan bounding box spans too many blocks"};
-        if (ovf & OVF_VGCELLS) caps.vg_cells = grow_to(h_cnt->vg_cells_needed, 1u << 20);
+        if (ovf & OVF_VGCELLS) {   // only the bit count matters (radix-sort passes): next power of two
+            unsigned int v = 1u << 20;
+            while (v < h_cnt->vg_cells_needed && v < 0x80000000u) v <<= 1;
+            caps.vg_cells = v;
+        }
         if (ovf & OVF_RAW) caps.raw = grow_to(h_cnt->n_raw_frees, 1024);
         if (ovf & OVF_CELLS) caps.cells = grow_to(h_cnt->n_cells, 1u << 16);
         if (ovf & OVF_MEMBERS) caps.members = grow_to(h_cnt->n_members, 1024);

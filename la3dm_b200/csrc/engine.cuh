@@ -42,7 +42,7 @@ struct Map {
     Caps caps{};                    // logical capacities the scan kernels check against
     Caps alloc{};                   // what the buffers can hold (>= caps)
     DevBuf cloud;                   // uploaded scan (host entry point)
-    DevBuf sort_keys[2], sort_vals[2], run_start, cub_tmp, tiles, long_list, hit_cnt;
+    DevBuf sort_keys[2], sort_vals[2], run_start, cub_tmp, tiles, long_list, long_flags, hit_cnt;
     DevBuf hits_ds;                 // float4 voxel-grid output of the cloud
     DevBuf frees_raw;               // float4 beam samples
     DevBuf xy;                      // float4 training set (x,y,z,label)
@@ -50,6 +50,8 @@ struct Map {
     DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
     DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
     DevBuf test_id, plan;
+    DevBuf beam_tab;                // sample distances of beam_sample for the current free_resolution
+    float beam_tab_fr = 0.f;
     size_t cub_tmp_bytes = 0;
     unsigned int *d_mm = nullptr;   // [3][6] flipped min/max
     GridDesc *d_grid = nullptr;
@@ -82,6 +84,7 @@ struct Map {
     void init(int method, const la3dm_params &p, int device);
     void ensure_pool(size_t blocks);
     void ensure_workspace();
+    void ensure_beam_table(float fr);
     void invalidate_graph();
     void insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
                        float max_range, bool frontend_only);

@@ -59,6 +59,47 @@ __device__ inline void minmax_accumulate(const float *__restrict__ in, int strid
     }
 }
 
+// warp-level min/max of one point per lane into mm[0..2] (min) / mm[3..5] (max), flipped-uint encoding.
+// Every lane of the warp must call it; `valid` says whether this lane contributes.
+__device__ inline void warp_minmax3(bool valid, float x, float y, float z, unsigned int *mm) {
+    if (!__any_sync(0xffffffffu, valid)) return;
+    float mn[3] = {valid ? x : 3.402823466e+38f, valid ? y : 3.402823466e+38f, valid ? z : 3.402823466e+38f};
+    float mx[3] = {valid ? x : -3.402823466e+38f, valid ? y : -3.402823466e+38f, valid ? z : -3.402823466e+38f};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&mm[a], float_flip(mn[a]));
+            atomicMax(&mm[3 + a], float_flip(mx[a]));
+        }
+    }
+}
+
+// same for a per-lane box
+__device__ inline void warp_minmax_box(bool valid, float *mn, float *mx, unsigned int *mm) {
+    if (!__any_sync(0xffffffffu, valid)) return;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!valid) { mn[a] = 3.402823466e+38f; mx[a] = -3.402823466e+38f; }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&mm[a], float_flip(mn[a]));
+            atomicMax(&mm[3 + a], float_flip(mx[a]));
+        }
+    }
+}
+
 // getMinMax3D of a voxel-grid input
 template <int W>
 __global__ void k_vg_minmax(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c,
@@ -168,75 +209,221 @@ __global__ void k_vg_run_place(const unsigned int *__restrict__ keys, const unsi
 }
 
 // one thread per voxel: sequential fp32 sum in ascending input order, then / float(count)  (pcl CentroidPoint);
-// runs longer than kLongRun are handed to k_vg_long
+// runs longer than kMidRun are handed to k_vg_long (a warp each; a CTA each beyond kLongRun).
+// Pass 1 (free centroids = the tail of the training set) also feeds the training-set bounding box mm_xy.
 template <int W>
 __global__ void k_vg_centroid(const ScanArgs *__restrict__ A, ScanCounters *c, const float4 *__restrict__ frees_raw,
                               const unsigned int *__restrict__ vals, const unsigned int *__restrict__ run_start,
-                              const unsigned int *__restrict__ d_total, float4 *out, unsigned int *long_list) {
+                              const unsigned int *__restrict__ d_total, float4 *out, unsigned int *long_list,
+                              unsigned int *mm_xy) {
     const unsigned int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c->overflow || r >= *d_total) return;
-    const float *in; int stride; unsigned int n;
-    vg_source<W>(A, c, frees_raw, in, stride, n);
-    const unsigned int first = run_start[r], last = run_start[r + 1];
-    if (last - first > (unsigned int) kLongRun) {
-        const unsigned int slot = atomicAdd(&c->n_long_runs[W], 1u);
-        if (slot < (unsigned int) kMaxLongRuns) { long_list[slot] = r; return; }
+    bool done = false;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (!c->overflow && r < *d_total) {
+        const float *in; int stride; unsigned int n;
+        vg_source<W>(A, c, frees_raw, in, stride, n);
+        const unsigned int first = run_start[r], last = run_start[r + 1];
+        bool handed = false;
+        if (last - first > (unsigned int) kLongRun) {
+            const unsigned int slot = atomicAdd(&c->n_long_runs[W], 1u);
+            if (slot < (unsigned int) kMaxLongRuns) { long_list[slot] = r; handed = true; }
+        } else if (last - first > (unsigned int) kMidRun) {
+            const unsigned int slot = atomicAdd(&c->n_mid_runs[W], 1u);
+            if (slot < (unsigned int) kMaxMidRuns) { long_list[kMaxLongRuns + slot] = r; handed = true; }
+        }
+        if (!handed) {
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (unsigned int li = first; li < last; ++li) {
+                const float *p = in + (size_t) vals[li] * stride;
+                sx += p[0]; sy += p[1]; sz += p[2];
+            }
+            const float cnt = (float) (last - first);
+            const unsigned int off = W == 0 ? 0u : c->n_hits;
+            const float label = W == 0 ? 1.0f : A->free_label;
+            cx = sx / cnt; cy = sy / cnt; cz = sz / cnt;
+            out[off + r] = make_float4(cx, cy, cz, label);
+            done = true;
+        }
     }
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (unsigned int li = first; li < last; ++li) {
-        const float *p = in + (size_t) vals[li] * stride;
-        sx += p[0]; sy += p[1]; sz += p[2];
+    if (W == 1) {   // CTA-level box first: one set of global atomics per CTA
+        __shared__ unsigned int s_mm[6];
+        if (threadIdx.x < 6) s_mm[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+        __syncthreads();
+        warp_minmax3(done, cx, cy, cz, s_mm);
+        __syncthreads();
+        if (threadIdx.x < 3) { if (s_mm[threadIdx.x] != 0xFFFFFFFFu) atomicMin(&mm_xy[threadIdx.x], s_mm[threadIdx.x]); }
+        else if (threadIdx.x < 6) { if (s_mm[threadIdx.x] != 0u) atomicMax(&mm_xy[threadIdx.x], s_mm[threadIdx.x]); }
     }
-    const float cnt = (float) (last - first);
-    const unsigned int off = W == 0 ? 0u : c->n_hits;
-    const float label = W == 0 ? 1.0f : A->free_label;
-    out[off + r] = make_float4(sx / cnt, sy / cnt, sz / cnt, label);
 }
 
-// long runs: a CTA stages the run through shared memory chunk by chunk; three lanes (x, y, z) add the chunk in
-// order.  A chunk made of one repeated point (the sensor origin, pushed once per hit) is added with add_repeat.
+// Long runs.  The sorted array is cut into aligned sub-chunks of kSub positions; k_vg_long_flags (whole grid) records
+// for every sub-chunk that lies inside a long run whether it is one point repeated (the sensor origin is pushed once
+// per hit, so its voxel holds n_hits copies).  k_vg_long then walks each long run in order with one CTA: consecutive
+// repeated-point sub-chunks are added with ONE add_repeat (exact, no loads), anything else is staged through shared
+// memory and added element by element by three lanes (x, y, z).  Medium runs get one warp each.
 constexpr int kLongThreads = 512;
-constexpr int kLongChunk = 2048;
+constexpr int kSub = 256;                      // points per sub-chunk (8 per lane)
+constexpr int kMidSub = 128;                   // points a warp stages at a time for a medium run
+constexpr int kSubsPerPass = 1024;             // sub-chunk flags staged in shared memory at a time
 
 template <int W>
 __global__ void __launch_bounds__(kLongThreads)
-k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, const float4 *__restrict__ frees_raw,
-          const unsigned int *__restrict__ vals, const unsigned int *__restrict__ run_start, float4 *out,
-          const unsigned int *__restrict__ long_list) {
-    __shared__ float sc[3][kLongChunk];
+k_vg_long_flags(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c,
+                const float4 *__restrict__ frees_raw, const unsigned int *__restrict__ vals,
+                const unsigned int *__restrict__ run_start, const unsigned int *__restrict__ long_list,
+                float *lf_first, unsigned char *lf_same, unsigned int n_sub_cap) {
     if (c->overflow) return;
     const unsigned int nl = min(c->n_long_runs[W], (unsigned int) kMaxLongRuns);
     const float *in; int stride; unsigned int n;
     vg_source<W>(A, c, frees_raw, in, stride, n);
+    const int lane = threadIdx.x & 31;
+    const unsigned int gw = (blockIdx.x * kLongThreads + threadIdx.x) >> 5, n_w = gridDim.x * (kLongThreads / 32);
+    for (unsigned int idx = 0; idx < nl; ++idx) {
+        const unsigned int r = long_list[idx];
+        const unsigned int g0 = (run_start[r] + kSub - 1) / kSub, g1 = run_start[r + 1] / kSub;   // whole sub-chunks
+        for (unsigned int g = g0 + gw; g < g1 && g < n_sub_cap; g += n_w) {
+            unsigned int vi[kSub / 32];
+#pragma unroll
+            for (int k = 0; k < kSub / 32; ++k) vi[k] = vals[g * kSub + lane + 32 * k];
+            float px[kSub / 32], py[kSub / 32], pz[kSub / 32];
+#pragma unroll
+            for (int k = 0; k < kSub / 32; ++k) {
+                const float *p = in + (size_t) vi[k] * stride;
+                px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+            }
+            const float fx = __shfl_sync(0xffffffffu, px[0], 0), fy = __shfl_sync(0xffffffffu, py[0], 0),
+                        fz = __shfl_sync(0xffffffffu, pz[0], 0);
+            bool eq = true;
+#pragma unroll
+            for (int k = 0; k < kSub / 32; ++k)
+                eq = eq && __float_as_uint(px[k]) == __float_as_uint(fx) && __float_as_uint(py[k]) == __float_as_uint(fy) &&
+                     __float_as_uint(pz[k]) == __float_as_uint(fz);
+            eq = __all_sync(0xffffffffu, eq);
+            if (lane == 0) {
+                lf_first[3 * (size_t) g] = fx; lf_first[3 * (size_t) g + 1] = fy; lf_first[3 * (size_t) g + 2] = fz;
+                lf_same[g] = eq ? 1 : 0;
+            }
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kLongThreads, 1)
+k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, const float4 *__restrict__ frees_raw,
+          const unsigned int *__restrict__ vals, const unsigned int *__restrict__ run_start, float4 *out,
+          const unsigned int *__restrict__ long_list, const float *__restrict__ lf_first,
+          const unsigned char *__restrict__ lf_same, unsigned int n_sub_cap, unsigned int *mm_xy) {
+    __shared__ float first[kSubsPerPass][3];   // the sub-chunk's first point
+    __shared__ unsigned char same[kSubsPerPass];
+    __shared__ float stage[3][kSub];
+    __shared__ float wstage[kLongThreads / 32][3][kMidSub];
+    if (c->overflow) return;
+    const unsigned int nl = min(c->n_long_runs[W], (unsigned int) kMaxLongRuns);
+    const unsigned int nm = min(c->n_mid_runs[W], (unsigned int) kMaxMidRuns);
+    const float *in; int stride; unsigned int n;
+    vg_source<W>(A, c, frees_raw, in, stride, n);
     const unsigned int off = W == 0 ? 0u : c->n_hits;
     const float label = W == 0 ? 1.0f : A->free_label;
-    for (unsigned int idx = blockIdx.x; idx < nl; idx += gridDim.x) {
-        const unsigned int r = long_list[idx];
-        const unsigned int first = run_start[r], last = run_start[r + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- medium runs: one warp each, staged kMidSub points at a time
+    for (unsigned int idx = blockIdx.x * (kLongThreads / 32) + warp; idx < nm; idx += gridDim.x * (kLongThreads / 32)) {
+        const unsigned int r = long_list[kMaxLongRuns + idx];
+        const unsigned int run_first = run_start[r], run_last = run_start[r + 1];
         float acc = 0.f;
-        for (unsigned int c0 = first; c0 < last; c0 += kLongChunk) {
-            const unsigned int m = min((unsigned int) kLongChunk, last - c0);
-            const float *p0 = in + (size_t) vals[c0] * stride;
-            const unsigned int r0 = __float_as_uint(p0[0]), r1 = __float_as_uint(p0[1]), r2 = __float_as_uint(p0[2]);
-            int same = 1;
-            for (unsigned int j = threadIdx.x; j < m; j += kLongThreads) {
-                const float *p = in + (size_t) vals[c0 + j] * stride;
-                const float x = p[0], y = p[1], z = p[2];
-                sc[0][j] = x; sc[1][j] = y; sc[2][j] = z;
-                same &= (__float_as_uint(x) == r0) & (__float_as_uint(y) == r1) & (__float_as_uint(z) == r2);
+        for (unsigned int s0 = run_first; s0 < run_last; s0 += kMidSub) {
+            const unsigned int m = min((unsigned int) kMidSub, run_last - s0);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kMidSub / 32; ++k) {
+                const unsigned int j = lane + 32 * k;
+                if (j < m) {
+                    const float *p = in + (size_t) vals[s0 + j] * stride;
+                    wstage[warp][0][j] = p[0]; wstage[warp][1][j] = p[1]; wstage[warp][2][j] = p[2];
+                }
             }
-            const int all_same = __syncthreads_and(same);
-            if (threadIdx.x < 3) {
-                const float *v = sc[threadIdx.x];
-                if (all_same) acc = add_repeat(acc, v[0], m);
-                else
-                    for (unsigned int j = 0; j < m; ++j) acc += v[j];
+            __syncwarp();
+            if (lane < 3) {
+                const float *v = wstage[warp][lane];
+                for (unsigned int j = 0; j < m; ++j) acc += v[j];
             }
-            __syncthreads();
         }
         float *o = reinterpret_cast<float *>(out + off + r);
-        if (threadIdx.x < 3) o[threadIdx.x] = acc / (float) (last - first);
-        else if (threadIdx.x == 3) o[3] = label;
+        if (lane < 3) {
+            const float v = acc / (float) (run_last - run_first);
+            o[lane] = v;
+            if (W == 1) { atomicMin(&mm_xy[lane], float_flip(v)); atomicMax(&mm_xy[3 + lane], float_flip(v)); }
+        } else if (lane == 3) o[3] = label;
+    }
+    // ---- long runs: one CTA each
+    for (unsigned int idx = blockIdx.x; idx < nl; idx += gridDim.x) {
+        const unsigned int r = long_list[idx];
+        const unsigned int run_first = run_start[r], run_last = run_start[r + 1];
+        const unsigned int g0 = min((run_first + kSub - 1) / kSub, n_sub_cap), g1 = min(run_last / kSub, n_sub_cap);
+        float acc = 0.f;
+        // pieces: head [run_first, g0 * kSub), whole sub-chunks g0 .. g1 - 1, tail [g1 * kSub, run_last)
+        unsigned int pos = run_first;
+        unsigned int g = g0;
+        while (pos < run_last) {
+            if (g < g1 && pos == g * kSub) {
+                const unsigned int nb = min(g1 - g, (unsigned int) kSubsPerPass);
+                __syncthreads();
+                for (unsigned int j = threadIdx.x; j < nb; j += kLongThreads) {
+                    first[j][0] = lf_first[3 * (size_t) (g + j)]; first[j][1] = lf_first[3 * (size_t) (g + j) + 1];
+                    first[j][2] = lf_first[3 * (size_t) (g + j) + 2];
+                    same[j] = lf_same[g + j];
+                }
+                __syncthreads();
+                for (unsigned int sc = 0; sc < nb; ++sc) {
+                    if (same[sc]) {
+                        // merge the following sub-chunks that repeat the same point: one add_repeat for all of them
+                        unsigned int m = kSub;
+                        const unsigned int f0 = __float_as_uint(first[sc][0]), f1 = __float_as_uint(first[sc][1]),
+                                           f2 = __float_as_uint(first[sc][2]);
+                        while (sc + 1 < nb && same[sc + 1] && __float_as_uint(first[sc + 1][0]) == f0 &&
+                               __float_as_uint(first[sc + 1][1]) == f1 && __float_as_uint(first[sc + 1][2]) == f2) {
+                            ++sc;
+                            m += kSub;
+                        }
+                        if (threadIdx.x < 3) acc = add_repeat(acc, first[sc][threadIdx.x], m);
+                    } else {
+                        const unsigned int s0 = (g + sc) * kSub;
+                        if (threadIdx.x < kSub) {
+                            const float *p = in + (size_t) vals[s0 + threadIdx.x] * stride;
+                            stage[0][threadIdx.x] = p[0]; stage[1][threadIdx.x] = p[1]; stage[2][threadIdx.x] = p[2];
+                        }
+                        __syncthreads();
+                        if (threadIdx.x < 3) {
+                            const float *v = stage[threadIdx.x];
+                            for (unsigned int j = 0; j < (unsigned int) kSub; ++j) acc += v[j];
+                        }
+                        __syncthreads();
+                    }
+                }
+                g += nb;
+                pos = g * kSub;
+            } else {
+                // head, tail, or sub-chunks beyond the flag capacity: staged
+                const unsigned int end = (g < g1) ? g * kSub : run_last;
+                const unsigned int m = min(end - pos, (unsigned int) kSub);
+                if (threadIdx.x < m) {
+                    const float *p = in + (size_t) vals[pos + threadIdx.x] * stride;
+                    stage[0][threadIdx.x] = p[0]; stage[1][threadIdx.x] = p[1]; stage[2][threadIdx.x] = p[2];
+                }
+                __syncthreads();
+                if (threadIdx.x < 3) {
+                    const float *v = stage[threadIdx.x];
+                    for (unsigned int j = 0; j < m; ++j) acc += v[j];
+                }
+                __syncthreads();
+                pos += m;
+            }
+        }
+        float *o = reinterpret_cast<float *>(out + off + r);
+        if (threadIdx.x < 3) {
+            const float v = acc / (float) (run_last - run_first);
+            o[threadIdx.x] = v;
+            if (W == 1) { atomicMin(&mm_xy[threadIdx.x], float_flip(v)); atomicMax(&mm_xy[3 + threadIdx.x], float_flip(v)); }
+        } else if (threadIdx.x == 3) o[3] = label;
     }
 }
 
@@ -253,29 +440,39 @@ __device__ inline unsigned int hit_free_count(const float4 h, const ScanArgs *A)
     }
     const float l = (float) sqrt((double) s);
     const float fr = A->fr;
-    unsigned int cnt = 1;                                   // the origin
-    float d = fr;
-    while (d < l) { ++cnt; d += fr; }
+    // number of e with beam_tab[e] < l (the table is non-decreasing); beyond the table continue the accumulation
+    const float *__restrict__ tab = A->beam_tab;
+    unsigned int lo = 0, hi = A->beam_tab_n;
+    while (lo < hi) {
+        const unsigned int mid = (lo + hi) >> 1;
+        if (tab[mid] < l) lo = mid + 1; else hi = mid;
+    }
+    unsigned int cnt = 1 + lo;                              // the origin + regular samples
+    if (lo == A->beam_tab_n) {
+        float d = tab[lo - 1] + fr;
+        while (d < l) { ++cnt; const float nd = d + fr; if (nd == d) break; d = nd; }
+    }
     if (l > fr) ++cnt;
     return cnt;
 }
 
-// tile_sums[tile] = (kept hits << 32) | free points of the tile; hit_cnt[i] = per-hit count (0 = dropped)
-__global__ void k_hit_count(const float4 *__restrict__ hits, const ScanCounters *__restrict__ c,
-                            const ScanArgs *__restrict__ A, unsigned int *hit_cnt, unsigned long long *tile_sums) {
+// tile_sums[tile] = (kept hits << 32) | free points of the tile (kHitTile hits, one per thread);
+// hit_cnt[i] = per-hit count (0 = dropped)
+constexpr int kHitTile = 256;
+
+__global__ void __launch_bounds__(kHitTile)
+k_hit_count(const float4 *__restrict__ hits, const ScanCounters *__restrict__ c, const ScanArgs *__restrict__ A,
+            unsigned int *hit_cnt, unsigned long long *tile_sums) {
     __shared__ unsigned long long s_sum;
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
     const unsigned int n = c->overflow ? 0u : c->n_ds_hits;
     unsigned long long acc = 0;
-    // strided over the tile so that the float4 loads coalesce; hit_cnt keeps hit order
-    for (int k = 0; k < kTileItems; ++k) {
-        const unsigned int i = blockIdx.x * kTile + k * kTileThreads + threadIdx.x;
-        if (i < n) {
-            const unsigned int cnt = hit_free_count(hits[i], A);
-            hit_cnt[i] = cnt;
-            if (cnt) acc += (1ull << 32) | (unsigned long long) cnt;
-        }
+    const unsigned int i = blockIdx.x * kHitTile + threadIdx.x;
+    if (i < n) {
+        const unsigned int cnt = hit_free_count(hits[i], A);
+        hit_cnt[i] = cnt;
+        if (cnt) acc = (1ull << 32) | (unsigned long long) cnt;
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&s_sum, acc);
@@ -283,11 +480,17 @@ __global__ void k_hit_count(const float4 *__restrict__ hits, const ScanCounters 
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = s_sum;
 }
 
-// writes the kept hits (label 1) to xy[0 .. n_hits) and every free point to frees_raw, in the reference's push order
-__global__ void k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__restrict__ A,
-                           const unsigned int *__restrict__ hit_cnt, const unsigned long long *__restrict__ tile_sums,
-                           unsigned int n_tiles, float4 *xy, float4 *frees, unsigned int raw_cap) {
+// writes the kept hits (label 1) to xy[0 .. n_hits) and every free point to frees_raw, in the reference's push order.
+// Positions come from a scan over the hits; the samples of one hit are then written by a whole warp (contiguous
+// 16-byte stores).  Sample e of a beam sits at d_e = fr + fr + ... (e fp32 additions, :451-455) = add_repeat(fr, fr, e).
+__global__ void __launch_bounds__(kHitTile)
+k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__restrict__ A,
+           const unsigned int *__restrict__ hit_cnt, const unsigned long long *__restrict__ tile_sums,
+           unsigned int n_tiles, float4 *xy, float4 *frees, unsigned int raw_cap, unsigned int *mm_raw,
+           unsigned int *mm_xy) {
     __shared__ unsigned long long smem[66];
+    __shared__ unsigned long long s_pos[kHitTile];
+    __shared__ unsigned int s_cnt[kHitTile];
     const unsigned int n = c->overflow ? 0u : c->n_ds_hits;
     unsigned long long prefix, total;
     block_tile_prefix(tile_sums, blockIdx.x, n_tiles, smem, prefix, total);
@@ -298,40 +501,55 @@ __global__ void k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, con
         if (n_raw > raw_cap) atomicOr(&c->overflow, OVF_RAW);
     }
     if (n_raw > raw_cap) return;
-    const unsigned int base = blockIdx.x * kTile + threadIdx.x * kTileItems;
-    unsigned long long mine = 0;
-    unsigned int cnts[kTileItems];
-#pragma unroll
-    for (int k = 0; k < kTileItems; ++k) {
-        const unsigned int i = base + k;
-        cnts[k] = i < n ? hit_cnt[i] : 0u;
-        if (cnts[k]) mine += (1ull << 32) | (unsigned long long) cnts[k];
-    }
+    const unsigned int i = blockIdx.x * kHitTile + threadIdx.x;
+    const unsigned int cnt = i < n ? hit_cnt[i] : 0u;
     unsigned long long cta_total;
-    unsigned long long pos = prefix + block_exclusive_scan(mine, smem, cta_total);
+    const unsigned long long mine = cnt ? ((1ull << 32) | (unsigned long long) cnt) : 0ull;
+    s_pos[threadIdx.x] = prefix + block_exclusive_scan(mine, smem, cta_total);
+    s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
     const float ox = A->ox, oy = A->oy, oz = A->oz, fr = A->fr;
-#pragma unroll 1
-    for (int k = 0; k < kTileItems; ++k) {
-        if (!cnts[k]) continue;
-        const float4 h = hits[base + k];
-        xy[(unsigned int) (pos >> 32)] = make_float4(h.x, h.y, h.z, 1.0f);                 // :399
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // bounding boxes on the fly: the free samples (getMinMax3D of the second voxel grid) and the kept hits (their part
+    // of the training-set bbox, src/bgkoctomap/bgkoctomap.cpp:464-484)
+    float smn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, smx[3] = {-smn[0], -smn[0], -smn[0]};
+    float hmn[3] = {smn[0], smn[0], smn[0]}, hmx[3] = {-smn[0], -smn[0], -smn[0]};
+    bool any_s = false, any_h = false;
+    for (int h = warp; h < kHitTile; h += kHitTile / 32) {
+        const unsigned int ch = s_cnt[h];
+        if (!ch) continue;
+        const unsigned long long pos = s_pos[h];
+        const float4 hit = hits[blockIdx.x * kHitTile + h];
         float4 *out = frees + (unsigned int) (pos & 0xFFFFFFFFull);
-        pos += (1ull << 32) | (unsigned long long) cnts[k];
-        *out++ = make_float4(ox, oy, oz, 0.f);                                             // :404
+        if (lane == 0) {
+            xy[(unsigned int) (pos >> 32)] = make_float4(hit.x, hit.y, hit.z, 1.0f);       // :399
+            out[0] = make_float4(ox, oy, oz, 0.f);                                        // :404
+            hmn[0] = fminf(hmn[0], hit.x); hmx[0] = fmaxf(hmx[0], hit.x);
+            hmn[1] = fminf(hmn[1], hit.y); hmx[1] = fmaxf(hmx[1], hit.y);
+            hmn[2] = fminf(hmn[2], hit.z); hmx[2] = fmaxf(hmx[2], hit.z);
+            smn[0] = fminf(smn[0], ox); smx[0] = fmaxf(smx[0], ox);
+            smn[1] = fminf(smn[1], oy); smx[1] = fmaxf(smx[1], oy);
+            smn[2] = fminf(smn[2], oz); smx[2] = fmaxf(smx[2], oz);
+            any_h = any_s = true;
+        }
         // beam_sample preamble (:437-449)
-        const float dx = h.x - ox, dy = h.y - oy, dz = h.z - oz;
+        const float dx = hit.x - ox, dy = hit.y - oy, dz = hit.z - oz;
         const float l = (float) sqrt((double) (dx * dx + dy * dy + dz * dz));
         const float nx = dx / l, ny = dy / l, nz = dz / l;
-        float d = fr;
-        while (d < l) {
-            *out++ = make_float4(ox + nx * d, oy + ny * d, oz + nz * d, 0.f);               // :453
-            d += fr;
-        }
-        if (l > fr) {
-            const float e = l - fr;
-            *out++ = make_float4(ox + nx * e, oy + ny * e, oz + nz * e, 0.f);               // :457
+        const unsigned int tail = l > fr ? 1u : 0u;
+        const unsigned int n_reg = ch - 1u - tail;                                        // samples with d < l (:451-455)
+        for (unsigned int e = lane; e < ch - 1u; e += 32) {
+            const float d = e < n_reg ? (e < A->beam_tab_n ? A->beam_tab[e] : add_repeat(fr, fr, e)) : l - fr;   // :453 | :457
+            const float sx = ox + nx * d, sy = oy + ny * d, sz = oz + nz * d;
+            out[1 + e] = make_float4(sx, sy, sz, 0.f);
+            smn[0] = fminf(smn[0], sx); smx[0] = fmaxf(smx[0], sx);
+            smn[1] = fminf(smn[1], sy); smx[1] = fmaxf(smx[1], sy);
+            smn[2] = fminf(smn[2], sz); smx[2] = fmaxf(smx[2], sz);
+            any_s = true;
         }
     }
+    warp_minmax_box(any_s, smn, smx, mm_raw);
+    warp_minmax_box(any_h, hmn, hmx, mm_xy);
 }
 
 __global__ void k_finish_train(ScanCounters *c) {
@@ -354,7 +572,7 @@ void Map::enqueue_voxel_grid(int which) {
     cub::DoubleBuffer<unsigned int> dk(sort_keys[0].as<unsigned int>(), sort_keys[1].as<unsigned int>());
     cub::DoubleBuffer<unsigned int> dv(sort_vals[0].as<unsigned int>(), sort_vals[1].as<unsigned int>());
     unsigned int *tile_sums = tiles.as<unsigned int>();
-    unsigned int *llist = long_list.as<unsigned int>() + (size_t) which * kMaxLongRuns;
+    unsigned int *llist = long_list.as<unsigned int>() + (size_t) which * (kMaxLongRuns + kMaxMidRuns);
     unsigned int *runs = run_start.as<unsigned int>();
     const float4 *fr = frees_raw.as<float4>();
     const int grid = ceil_div(cap, kThreads);
@@ -366,10 +584,10 @@ void Map::enqueue_voxel_grid(int which) {
         k_vg_minmax<0><<<mm_grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, mm);
         k_vg_keys<0><<<grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, mm, dk.Current(), dv.Current(), cap,
                                                     caps.vg_cells);
-    } else {
-        k_vg_minmax<1><<<mm_grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, mm);
+    } else {   // the bounding box of the free samples was accumulated by k_hit_fill
         k_vg_keys<1><<<grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, mm, dk.Current(), dv.Current(), cap,
                                                     caps.vg_cells);
+        --launches;
     }
     LA3DM_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp, dk, dv, (int) cap, 0, end_bit, stream));
     const unsigned int *ks = dk.Current(), *vs = dv.Current();
@@ -378,29 +596,40 @@ void Map::enqueue_voxel_grid(int which) {
     k_run_count<<<n_tiles, kTileThreads, 0, stream>>>(ks, d_n, cap, tile_sums, d_cnt);
     k_vg_run_place<<<n_tiles, kTileThreads, 0, stream>>>(ks, d_n, cap, tile_sums, (unsigned int) n_tiles, runs,
                                                          d_total, d_cnt);
-    const int long_grid = 64;
+    const int long_grid = num_sms;
+    const unsigned int n_sub_cap = cap / kSub + 1;
+    float *lf_first = long_flags.as<float>();
+    unsigned char *lf_same = reinterpret_cast<unsigned char *>(lf_first + 3 * (size_t) n_sub_cap);
+    unsigned int *mm_xy = d_mm + 12;
     if (which == 0) {
         k_vg_centroid<0><<<grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, d_total, hits_ds.as<float4>(),
-                                                        llist);
-        k_vg_long<0><<<long_grid, kLongThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, hits_ds.as<float4>(), llist);
+                                                        llist, mm_xy);
+        k_vg_long_flags<0><<<long_grid, kLongThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, llist, lf_first,
+                                                                   lf_same, n_sub_cap);
+        k_vg_long<0><<<long_grid, kLongThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, hits_ds.as<float4>(), llist,
+                                                             lf_first, lf_same, n_sub_cap, mm_xy);
     } else {
-        k_vg_centroid<1><<<grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, d_total, xy.as<float4>(), llist);
-        k_vg_long<1><<<long_grid, kLongThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, xy.as<float4>(), llist);
+        k_vg_centroid<1><<<grid, kThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, d_total, xy.as<float4>(), llist,
+                                                        mm_xy);
+        k_vg_long_flags<1><<<long_grid, kLongThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, llist, lf_first,
+                                                                   lf_same, n_sub_cap);
+        k_vg_long<1><<<long_grid, kLongThreads, 0, stream>>>(d_args, d_cnt, fr, vs, runs, xy.as<float4>(), llist,
+                                                             lf_first, lf_same, n_sub_cap, mm_xy);
     }
-    launches += 6 + 2 + (end_bit + 7) / 8;   // ours + CUB radix sort (histogram, exclusive sum, onesweep passes)
+    launches += 7 + 2 + (end_bit + 7) / 8;   // ours + CUB radix sort (histogram, exclusive sum, onesweep passes)
 }
 
 // BGK / GP front-end.  On completion (stream-ordered): xy[0..n_train) = hits (label 1) then free centroids (label
 // 0 / -1) and d_cnt->{n_ds_hits, n_hits, n_raw_frees, n_frees, n_train} are set.
 void Map::enqueue_frontend_bgk() {
     enqueue_voxel_grid(0);
-    const int n_tiles = ceil_div(caps.points, kTile);
+    const int n_tiles = ceil_div(caps.points, kHitTile);
     unsigned long long *tile_sums = tiles.as<unsigned long long>();
-    k_hit_count<<<n_tiles, kTileThreads, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
-                                                      tile_sums);
-    k_hit_fill<<<n_tiles, kTileThreads, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
-                                                     tile_sums, (unsigned int) n_tiles, xy.as<float4>(),
-                                                     frees_raw.as<float4>(), caps.raw);
+    k_hit_count<<<n_tiles, kHitTile, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
+                                                  tile_sums);
+    k_hit_fill<<<n_tiles, kHitTile, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
+                                                 tile_sums, (unsigned int) n_tiles, xy.as<float4>(),
+                                                 frees_raw.as<float4>(), caps.raw, d_mm + 6, d_mm + 12);
     launches += 2;
     enqueue_voxel_grid(1);
     k_finish_train<<<1, 1, 0, stream>>>(d_cnt);

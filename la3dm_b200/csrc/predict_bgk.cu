@@ -44,14 +44,19 @@ struct UpdateParams {
     float var_thresh, occupied_thresh, free_thresh;
 };
 
-// Occupancy::update (bgkoctree_node.cpp:31-44); returns the new state
-__device__ __forceinline__ unsigned char bgk_update(float &a, float &b, float ybar, float kbar, const UpdateParams &P) {
-    a += ybar;
-    b += kbar - ybar;
+// state of a node from (m_A, m_B): the tail of Occupancy::update (bgkoctree_node.cpp:36-43, get_var: .h:60)
+__device__ __forceinline__ unsigned char bgk_classify(float a, float b, const UpdateParams &P) {
     const float var = (a * b) / ((a + b) * (a + b) * (a + b + 1.0f));
     if (var > P.var_thresh) return LA3DM_UNKNOWN;
     const float p = a / (a + b);
     return p > P.occupied_thresh ? LA3DM_OCCUPIED : (p < P.free_thresh ? LA3DM_FREE : LA3DM_UNKNOWN);
+}
+
+// Occupancy::update (bgkoctree_node.cpp:31-44); returns the new state
+__device__ __forceinline__ unsigned char bgk_update(float &a, float &b, float ybar, float kbar, const UpdateParams &P) {
+    a += ybar;
+    b += kbar - ybar;
+    return bgk_classify(a, b, P);
 }
 
 struct WarpSmem {
@@ -61,7 +66,7 @@ struct WarpSmem {
     unsigned int masks[kPtTile][2];     // lanes inside the support, per (point of the tile, slot)
 };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
               const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
               const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt) {
@@ -238,10 +243,10 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__
                         if (open) {
 #pragma unroll
                             for (int s = 0; s < 2; ++s) {
-                                if (node[s] >= 0 && kb[s] > 0.0f) {                      // bgkoctomap.cpp:332
-                                    state[s] = bgk_update(a[s], b[s], yb[s], kb[s], U) | 0x80;   // classified = true
-                                    touched[s] = 1;
-                                }
+                                // Occupancy::update's accumulation (bgkoctree_node.cpp:31-35), guarded by
+                                // kbar > 0 (bgkoctomap.cpp:332); the classification that follows it upstream only
+                                // survives for the last update of the scan and is done once, below
+                                if (node[s] >= 0 && kb[s] > 0.0f) { a[s] += yb[s]; b[s] += kb[s] - yb[s]; touched[s] = 1; }
                                 yb[s] = kb[s] = 0.f;
                             }
                         }
@@ -277,10 +282,7 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__
         if (open) {
 #pragma unroll
             for (int s = 0; s < 2; ++s)
-                if (node[s] >= 0 && kb[s] > 0.0f) {
-                    state[s] = bgk_update(a[s], b[s], yb[s], kb[s], U) | 0x80;
-                    touched[s] = 1;
-                }
+                if (node[s] >= 0 && kb[s] > 0.0f) { a[s] += yb[s]; b[s] += kb[s] - yb[s]; touched[s] = 1; }
         }
 
         // ---- write back into the staged record
@@ -289,7 +291,7 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__
         for (int s = 0; s < 2; ++s) {
             if (node[s] >= 0 && touched[s]) {
                 rab[node[s]] = make_float2(a[s], b[s]);
-                rst[node[s]] = state[s];
+                rst[node[s]] = bgk_classify(a[s], b[s], U) | 0x80;   // classified = true
                 ++updates;
                 any = true;
             }
