@@ -1,0 +1,277 @@
+/*
+ * la3dm_b200 -- C++ facade with the reference's class and method names over the C ABI (include/la3dm_b200.h).
+ *
+ * Drop-in for the part of
+ *   la3dm::BGKOctoMap    (include/bgkoctomap/bgkoctomap.h:50-58, 82-84, 89, 217-319)
+ *   la3dm::BGKLOctoMap   (include/bgkloctomap/bgkloctomap.h:53-61)
+ *   la3dm::BGKLVOctoMap  (include/bgklvoctomap/bgklvoctomap.h:52-62)
+ *   la3dm::GPOctoMap     (include/gpoctomap/gpoctomap.h:50-52)
+ * that the reference's nodes use: constructor, insert_pointcloud, get_bbox, begin_leaf()/end_leaf() with
+ * get_loc / get_size / get_node / get_pruned_locs, get_resolution / get_block_depth / get_block_size, search.
+ * Header only; link with -lla3dm_b200.  All map state lives on the GPU; the leaf iterator walks a host mirror that is
+ * refreshed lazily (one la3dm_export_leaves call) the first time it is used after an insert.
+ *
+ * The cloud / point types are template parameters so that the header does not depend on PCL:
+ *   Cloud  : has `.points` (contiguous container of structs that start with float x, y, z), e.g.
+ *            pcl::PointCloud<pcl::PointXYZ> (16-byte stride);
+ *   Point  : has x(), y(), z() and a (float, float, float) constructor, e.g. la3dm::point3f.
+ * In a tree that still has the reference's headers, define LA3DM_B200_NAMESPACE to something else than `la3dm` to
+ * keep both implementations side by side.
+ */
+#ifndef LA3DM_B200_OCTOMAP_H
+#define LA3DM_B200_OCTOMAP_H
+
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../la3dm_b200.h"
+
+#ifndef LA3DM_B200_NAMESPACE
+#define LA3DM_B200_NAMESPACE la3dm
+#endif
+
+namespace LA3DM_B200_NAMESPACE {
+
+/// enum class State (include/bgkoctomap/bgkoctree_node.h:10-12; BGKLV: bgklvoctree_node.h:11-13)
+enum class State : char { FREE, OCCUPIED, UNKNOWN, PRUNED };
+enum class LVState : char { FREE, OCCUPIED, UNKNOWN, UNCERTAIN, PRUNED };
+
+typedef int64_t BlockHashKey;
+
+/// minimal stand-in for la3dm::point3f (include/common/point3f.h) for trees that do not have it
+struct vec3f {
+    float v[3];
+    vec3f() : v{0.f, 0.f, 0.f} {}
+    vec3f(float x, float y, float z) : v{x, y, z} {}
+    float &x() { return v[0]; }
+    float &y() { return v[1]; }
+    float &z() { return v[2]; }
+    const float &x() const { return v[0]; }
+    const float &y() const { return v[1]; }
+    const float &z() const { return v[2]; }
+};
+
+/// what LeafIterator::get_node() returns: read-only view of one Occupancy (include/bgkoctomap/bgkoctree_node.h:17-81)
+class OcTreeNode {
+public:
+    explicit OcTreeNode(const la3dm_leaf *l = nullptr) : l_(l) {}
+    float get_prob() const { return l_ ? l_->prob : 0.5f; }
+    float get_var() const { return l_ ? l_->var : 0.f; }
+    State get_state() const { return l_ ? static_cast<State>(l_->state) : State::UNKNOWN; }
+    int get_state_raw() const { return l_ ? l_->state : (int) LA3DM_UNKNOWN; }   /* BGKLV numbering: LVState */
+    bool classified() const { return l_ && l_->classified; }
+    float get_a() const { return l_ ? l_->a : 0.f; }   /* m_A | GP m_ivar */
+    float get_b() const { return l_ ? l_->b : 0.f; }   /* m_B | GP ivar   */
+private:
+    const la3dm_leaf *l_;
+};
+
+template <int METHOD>
+class OctoMapT {
+public:
+    ~OctoMapT() { if (h_) la3dm_destroy(h_); }
+    OctoMapT(const OctoMapT &) = delete;
+    OctoMapT &operator=(const OctoMapT &) = delete;
+
+    float get_resolution() const { return params_.resolution; }
+    float get_block_depth() const { return (float) params_.block_depth; }   /* float upstream too (bgkoctomap.h:70) */
+    float get_block_size() const { return (float) std::pow(2, params_.block_depth - 1) * params_.resolution; }
+
+    /// insert_pointcloud (include/bgkoctomap/bgkoctomap.h:82-84)
+    template <class Cloud, class Point>
+    void insert_pointcloud(const Cloud &cloud, const Point &origin, float ds_resolution, float free_res = 2.0f,
+                           float max_range = -1) {
+        const float o[3] = {origin.x(), origin.y(), origin.z()};
+        const size_t n = cloud.points.size();
+        const float *xyz = n ? reinterpret_cast<const float *>(&cloud.points[0]) : nullptr;
+        check(la3dm_insert_pointcloud(h_, xyz, n, sizeof(cloud.points[0]), o, ds_resolution, free_res, max_range));
+        dirty_ = true;
+    }
+    /// same, from a raw host array of n records of stride_bytes that start with float x, y, z
+    void insert_pointcloud(const float *xyz, size_t n, size_t stride_bytes, const float origin[3], float ds_resolution,
+                           float free_res = 2.0f, float max_range = -1) {
+        check(la3dm_insert_pointcloud(h_, xyz, n, stride_bytes, origin, ds_resolution, free_res, max_range));
+        dirty_ = true;
+    }
+
+    /// get_bbox (src/bgkoctomap/bgkoctomap.cpp:368-381)
+    template <class Point>
+    void get_bbox(Point &lim_min, Point &lim_max) const {
+        float mn[3], mx[3];
+        check(la3dm_get_bbox(h_, mn, mx));
+        lim_min = Point(mn[0], mn[1], mn[2]);
+        lim_max = Point(mx[0], mx[1], mx[2]);
+    }
+
+    la3dm_scan_stats last_stats() const {
+        la3dm_scan_stats s;
+        la3dm_last_stats(h_, &s);
+        return s;
+    }
+    size_t num_blocks() const { return (size_t) la3dm_num_blocks(h_); }
+    la3dm_map *handle() const { return h_; }
+
+    /// LeafIterator (include/bgkoctomap/bgkoctomap.h:217-307).  Order: blocks by key, leaves by (depth, index).
+    class LeafIterator {
+    public:
+        LeafIterator(const OctoMapT *m, size_t i) : m_(m), i_(i) {}
+        bool operator==(const LeafIterator &o) const { return i_ == o.i_; }
+        bool operator!=(const LeafIterator &o) const { return i_ != o.i_; }
+        LeafIterator &operator++() { ++i_; return *this; }
+        LeafIterator operator++(int) { LeafIterator r(*this); ++i_; return r; }
+        OcTreeNode operator*() const { return OcTreeNode(&m_->leaves_[i_]); }
+        OcTreeNode get_node() const { return OcTreeNode(&m_->leaves_[i_]); }
+        vec3f get_loc() const { const la3dm_leaf &l = m_->leaves_[i_]; return vec3f(l.x, l.y, l.z); }
+        float get_size() const { return m_->leaves_[i_].size; }
+        const la3dm_leaf &raw() const { return m_->leaves_[i_]; }
+        /// centres of the finest voxels a pruned leaf covers (bgkoctomap.h:265-283, same float stepping)
+        std::vector<vec3f> get_pruned_locs() const {
+            std::vector<vec3f> out;
+            const la3dm_leaf &l = m_->leaves_[i_];
+            const float res = m_->params_.resolution, size = l.size;
+            const float x0 = l.x - size * 0.5 + res * 0.5, y0 = l.y - size * 0.5 + res * 0.5, z0 = l.z - size * 0.5 + res * 0.5;
+            const float x1 = l.x + size * 0.5, y1 = l.y + size * 0.5, z1 = l.z + size * 0.5;
+            for (float x = x0; x < x1; x += res)
+                for (float y = y0; y < y1; y += res)
+                    for (float z = z0; z < z1; z += res) out.emplace_back(x, y, z);
+            return out;
+        }
+    private:
+        const OctoMapT *m_;
+        size_t i_;
+    };
+    LeafIterator begin_leaf() const { refresh(); return LeafIterator(this, 0); }
+    LeafIterator end_leaf() const { refresh(); return LeafIterator(this, leaves_.size()); }
+    size_t num_leaves() const { refresh(); return leaves_.size(); }
+
+    /// search(x, y, z): the leaf whose cube holds the point (an UNKNOWN default node if the block does not exist).
+    /// The reference's Block::search is only right for block_depth 4; this one is right for any depth.
+    OcTreeNode search(float x, float y, float z) const {
+        refresh();
+        const BlockHashKey key = la3dm_block_to_hash_key(h_, x, y, z);
+        auto it = block_range_.find(key);
+        if (it == block_range_.end()) return OcTreeNode();
+        for (size_t i = it->second.first; i < it->second.second; ++i) {
+            const la3dm_leaf &l = leaves_[i];
+            const float h = l.size * 0.5f;
+            if (x >= l.x - h && x <= l.x + h && y >= l.y - h && y <= l.y + h && z >= l.z - h && z <= l.z + h)
+                return OcTreeNode(&l);
+        }
+        return OcTreeNode();
+    }
+    template <class Point>
+    OcTreeNode search(const Point &p) const { return search(p.x(), p.y(), p.z()); }
+
+protected:
+    explicit OctoMapT(const la3dm_params &p, int device = 0) : params_(p) {
+        const int rc = la3dm_create(METHOD, &params_, device, &h_);
+        if (rc != LA3DM_OK) {
+            const char *msg = la3dm_last_error(nullptr);
+            throw std::runtime_error(std::string("la3dm_b200: ") + (msg && *msg ? msg : la3dm_status_string(rc)));
+        }
+    }
+    void check(int rc) const {
+        if (rc != LA3DM_OK) throw std::runtime_error(std::string("la3dm_b200: ") + la3dm_last_error(h_));
+    }
+    void refresh() const {
+        if (!dirty_) return;
+        size_t n = 0;
+        check(la3dm_export_leaves(h_, nullptr, 0, &n));
+        leaves_.resize(n);
+        if (n) check(la3dm_export_leaves(h_, leaves_.data(), n, &n));
+        block_range_.clear();
+        for (size_t i = 0; i < n;) {
+            size_t j = i;
+            while (j < n && leaves_[j].block_key == leaves_[i].block_key) ++j;
+            block_range_[leaves_[i].block_key] = std::make_pair(i, j);
+            i = j;
+        }
+        dirty_ = false;
+    }
+
+    la3dm_params params_;
+    la3dm_map *h_ = nullptr;
+    mutable bool dirty_ = true;
+    mutable std::vector<la3dm_leaf> leaves_;
+    mutable std::unordered_map<BlockHashKey, std::pair<size_t, size_t>> block_range_;
+};
+
+inline la3dm_params make_bgk_params(float resolution, unsigned short block_depth, float sf2, float ell,
+                                    float free_thresh, float occupied_thresh, float var_thresh, float prior_A,
+                                    float prior_B) {
+    la3dm_params p = la3dm_params();
+    p.resolution = resolution; p.block_depth = block_depth; p.sf2 = sf2; p.ell = ell;
+    p.free_thresh = free_thresh; p.occupied_thresh = occupied_thresh; p.var_thresh = var_thresh;
+    p.prior_A = prior_A; p.prior_B = prior_B;
+    return p;
+}
+
+/// la3dm::BGKOctoMap (include/bgkoctomap/bgkoctomap.h:50-58); defaults of the no-argument constructor: bgkoctomap.cpp:22-31
+class BGKOctoMap : public OctoMapT<LA3DM_BGK> {
+public:
+    BGKOctoMap(float resolution, unsigned short block_depth, float sf2, float ell, float free_thresh,
+               float occupied_thresh, float var_thresh, float prior_A, float prior_B, int device = 0)
+        : OctoMapT(make_bgk_params(resolution, block_depth, sf2, ell, free_thresh, occupied_thresh, var_thresh, prior_A,
+                                   prior_B), device) {}
+    BGKOctoMap() : BGKOctoMap(0.1f, 4, 1.0f, 1.0f, 0.3f, 0.7f, 1.0f, 1.0f, 1.0f) {}
+};
+
+/// la3dm::BGKLOctoMap (include/bgkloctomap/bgkloctomap.h:53-61)
+class BGKLOctoMap : public OctoMapT<LA3DM_BGKL> {
+public:
+    BGKLOctoMap(float resolution, unsigned short block_depth, float sf2, float ell, float free_thresh,
+                float occupied_thresh, float var_thresh, float prior_A, float prior_B, int device = 0)
+        : OctoMapT(make_bgk_params(resolution, block_depth, sf2, ell, free_thresh, occupied_thresh, var_thresh, prior_A,
+                                   prior_B), device) {}
+    BGKLOctoMap() : BGKLOctoMap(0.1f, 4, 1.0f, 1.0f, 0.3f, 0.7f, 1.0f, 1.0f, 1.0f) {}
+};
+
+/// la3dm::BGKLVOctoMap (include/bgklvoctomap/bgklvoctomap.h:52-62)
+class BGKLVOctoMap : public OctoMapT<LA3DM_BGKLV> {
+public:
+    BGKLVOctoMap(float resolution, unsigned short block_depth, float sf2, float ell, float free_thresh,
+                 float occupied_thresh, float var_thresh, float prior_A, float prior_B, bool original_size, float MIN_W,
+                 int device = 0)
+        : OctoMapT(lv_params(resolution, block_depth, sf2, ell, free_thresh, occupied_thresh, var_thresh, prior_A,
+                             prior_B, original_size, MIN_W), device) {}
+private:
+    static la3dm_params lv_params(float resolution, unsigned short block_depth, float sf2, float ell, float free_thresh,
+                                  float occupied_thresh, float var_thresh, float prior_A, float prior_B,
+                                  bool original_size, float MIN_W) {
+        la3dm_params p = make_bgk_params(resolution, block_depth, sf2, ell, free_thresh, occupied_thresh, var_thresh,
+                                         prior_A, prior_B);
+        p.original_size = original_size ? 1 : 0;
+        p.min_W = MIN_W;
+        return p;
+    }
+};
+
+/// la3dm::GPOctoMap (include/gpoctomap/gpoctomap.h:50-52)
+class GPOctoMap : public OctoMapT<LA3DM_GP> {
+public:
+    GPOctoMap(float resolution, unsigned short block_depth, float sf2, float ell, float noise, float l, float min_var,
+              float max_var, float max_known_var, float free_thresh, float occupied_thresh, int device = 0)
+        : OctoMapT(gp_params(resolution, block_depth, sf2, ell, noise, l, min_var, max_var, max_known_var, free_thresh,
+                             occupied_thresh), device) {}
+    GPOctoMap() : GPOctoMap(0.1f, 4, 1.0f, 1.0f, 0.01f, 100.f, 0.001f, 1000.f, 0.02f, 0.3f, 0.7f) {}
+private:
+    static la3dm_params gp_params(float resolution, unsigned short block_depth, float sf2, float ell, float noise,
+                                  float l, float min_var, float max_var, float max_known_var, float free_thresh,
+                                  float occupied_thresh) {
+        la3dm_params p = la3dm_params();
+        p.resolution = resolution; p.block_depth = block_depth; p.sf2 = sf2; p.ell = ell; p.noise = noise; p.l = l;
+        p.min_var = min_var; p.max_var = max_var; p.max_known_var = max_known_var;
+        p.free_thresh = free_thresh; p.occupied_thresh = occupied_thresh;
+        return p;
+    }
+};
+
+}  // namespace LA3DM_B200_NAMESPACE
+
+#endif /* LA3DM_B200_OCTOMAP_H */
