@@ -350,7 +350,7 @@ __device__ inline void hash_insert(long long *hkeys, int *hvals, size_t mask, lo
 __global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs *__restrict__ A,
                        const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
                        const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask,
-                       long long *keys, NeighbourPlan *plan) {
+                       long long *keys, NeighbourPlan *plan, unsigned int *plan_db) {
     const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (c->overflow || t >= c->n_test_blocks) return;
     const unsigned int id = test_id[t];
@@ -377,7 +377,8 @@ __global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c
                                      (unsigned int) zz;
             const unsigned int d = cell_db[nid];
             if (d) { start = db_start[d - 1]; count = db_start[d] - start; }
-        }
+            if (plan_db) plan_db[(size_t) t * 8 + k] = d;      // data block index + 1 (GP: locates the regressor)
+        } else if (plan_db) plan_db[(size_t) t * 8 + k] = 0;
         pl.start[k] = start;
         pl.count[k] = count;
     }
@@ -463,6 +464,9 @@ void Map::enqueue_binning() {
                                                      test_bits.as<unsigned int>());
     launches += 8 + 2 + (end_bit + 7) / 8;
 
+    // GP: sizes of the per-data-block regressors -- every capacity check must come before k_plan touches the map
+    if (hp.method == LA3DM_GP) enqueue_gp_sizes();
+
     // test blocks, their slots in the map and their neighbour plans
     const int w_tiles = ceil_div(n_words, kThreads);
     const int prescanned = w_tiles > 1024 ? 1 : 0;
@@ -473,7 +477,8 @@ void Map::enqueue_binning() {
                                                    caps.tests);
     k_plan<<<ceil_div(caps.tests, kThreads), kThreads, 0, stream>>>(
         test_id.as<unsigned int>(), d_cnt, d_args, d_grid, cell_db.as<unsigned int>(), db_start.as<unsigned int>(),
-        hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>());
+        hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
+        hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr);
     launches += 3;
 }
 

@@ -1,0 +1,68 @@
+// la3dm_b200 -- pieces shared by the per-test-block predict kernels (one warp per block, block_depth <= 3):
+// staging of the block record in shared memory, leaf resolution, OcTree::prune and the write-back.
+#pragma once
+#include "engine.cuh"
+
+namespace la3dm_b200 {
+
+constexpr int kRecMax = 672;          // bytes of a depth-3 record: 73 * 8 + 73 -> 16-byte multiple
+
+// record -> shared memory (a fresh Block gets the default node everywhere: bgkoctree_node.h:34 / gpoctree_node.h:34)
+__device__ __forceinline__ void stage_record(uint4 *srec, const uint4 *grec, bool is_new, const DevParams &P, int lane) {
+    float2 *rab = reinterpret_cast<float2 *>(srec);
+    unsigned char *rb = reinterpret_cast<unsigned char *>(srec);
+    if (is_new) {
+        for (int n = lane; n < P.nodes; n += 32) { rab[n] = make_float2(P.def_a, P.def_b); rb[P.st_off + n] = LA3DM_UNKNOWN; }
+        for (int n = P.st_off + P.nodes + lane; n < P.rec_bytes; n += 32) rb[n] = 0;
+    } else {
+        for (int w = lane; w < (P.rec_bytes >> 4); w += 32) srec[w] = grec[w];
+    }
+}
+
+// Leaves of the block owned by this lane: finest slots lane and lane + 32; a slot whose ancestors were pruned resolves
+// to the coarser leaf (d, i), owned by the lane of its first finest descendant (is_leaf: bgkoctree.cpp:72-82).
+__device__ __forceinline__ void resolve_leaves(const unsigned char *rst, const DevParams &P, int lane, int node[2]) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int j = lane + 32 * s;
+        node[s] = -1;
+        if (j < P.finest) {
+            int d = P.depth - 1, i = j, shift = 0;
+            while (d > 0 && (rst[P.layer_off[d] + i] & 7) == kStPRUNED) { --d; i >>= 3; shift += 3; }
+            if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != kStPRUNED)) node[s] = P.layer_off[d] + i;
+        }
+    }
+}
+
+// OcTree::prune (bgkoctree.cpp:101-148) on the staged record: deepest layer first; 8 equal FREE/OCCUPIED siblings
+// collapse into the parent (copy of child 0's two floats and state -- `classified` is not copied,
+// bgkoctree_node.h:40-45); ends with a __syncwarp
+__device__ __forceinline__ void prune_record(float2 *rab, unsigned char *rst, const DevParams &P, int lane) {
+    for (int d = P.depth - 1; d > 0; --d) {
+        const int off = P.layer_off[d], poff = P.layer_off[d - 1];
+        const int groups = 1 << (3 * (d - 1));
+        for (int g = lane; g < groups; g += 32) {
+            const unsigned char s0 = rst[off + 8 * g] & 7;
+            if (s0 == LA3DM_FREE || s0 == LA3DM_OCCUPIED) {
+                bool same = true;
+#pragma unroll
+                for (int i = 1; i < 8; ++i) same = same && ((rst[off + 8 * g + i] & 7) == s0);
+                if (same) {
+                    rab[poff + g] = rab[off + 8 * g];
+                    rst[poff + g] = (rst[poff + g] & 0x80) | s0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rst[off + 8 * g + i] = (rst[off + 8 * g + i] & 0x80) | kStPRUNED;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void load_params(DevParams &Ps, const DevParams *Pg) {
+    if (threadIdx.x < sizeof(DevParams) / 4)
+        reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    __syncthreads();
+}
+
+}  // namespace la3dm_b200

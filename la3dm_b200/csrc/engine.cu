@@ -124,6 +124,7 @@ unsigned int grow_to(unsigned int need, unsigned int floor_) {
 }  // namespace
 
 size_t radix_sort_temp_bytes(unsigned int items);   // frontend.cu
+size_t scan_temp_bytes(unsigned int items);         // predict_gp.cu
 
 Map::~Map() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -232,6 +233,8 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     caps.cells = 1u << 16;
     caps.tests = 8192;
     caps.vg_cells = 1u << 20;
+    caps.gp_store = method == LA3DM_GP ? (1u << 22) : 0;
+    caps.gp_n_max = method == LA3DM_GP ? 160 : 0;
     ensure_pool(4096 + caps.tests);
     ensure_workspace();
     LA3DM_CUDA(cudaStreamSynchronize(stream));
@@ -285,7 +288,16 @@ void Map::ensure_workspace() {
     moved |= test_bits.reserve(((size_t) caps.cells / 32 + 2) * 4, stream);
     moved |= test_id.reserve((size_t) caps.tests * 4, stream);
     moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
-    const size_t tmp = radix_sort_temp_bytes((unsigned int) n_sort);
+    if (hp.method == LA3DM_GP) {
+        moved |= gp_sizes.reserve(((size_t) caps.members + 2) * 8, stream);
+        moved |= gp_off.reserve(((size_t) caps.members + 2) * 8, stream);
+        moved |= gp_store.reserve((size_t) caps.gp_store * 4, stream);
+        moved |= plan_db.reserve((size_t) caps.tests * 8 * 4, stream);
+        gp_ctas = num_sms * 2;
+        moved |= gp_scratch.reserve((size_t) gp_ctas * 4 * 2 * caps.gp_n_max * 64 * 4, stream);
+    }
+    const size_t tmp = std::max(radix_sort_temp_bytes((unsigned int) n_sort),
+                                hp.method == LA3DM_GP ? scan_temp_bytes(caps.members) : (size_t) 0);
     if (tmp > cub_tmp_bytes) { moved |= cub_tmp.reserve(tmp, stream); cub_tmp_bytes = tmp; }
     if (moved) invalidate_graph();
 }
@@ -368,6 +380,9 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (ovf & OVF_CELLS) caps.cells = grow_to(h_cnt->n_cells, 1u << 16);
         if (ovf & OVF_MEMBERS) caps.members = grow_to(h_cnt->n_members, 1024);
         if (ovf & OVF_TESTS) caps.tests = grow_to(h_cnt->n_test_blocks, 8192);
+        if (ovf & OVF_GPSTORE)
+            caps.gp_store = grow_to((unsigned int) std::min<unsigned long long>(h_cnt->gp_store_needed, 0x60000000ull), 1u << 22);
+        if (ovf & OVF_GPN) caps.gp_n_max = grow_to(h_cnt->gp_n_max, 160);
         caps.train = caps.points + caps.raw;
         if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }

@@ -50,6 +50,8 @@ struct Map {
     DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
     DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
     DevBuf test_id, plan;
+    DevBuf gp_sizes, gp_off, gp_store, gp_scratch, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
+    int gp_ctas = 0;
     DevBuf beam_tab;                // sample distances of beam_sample for the current free_resolution
     float beam_tab_fr = 0.f;
     size_t cub_tmp_bytes = 0;
@@ -94,6 +96,9 @@ struct Map {
     void enqueue_voxel_grid(int which);
     void enqueue_binning();
     void enqueue_predict();
+    void enqueue_gp();
+    void enqueue_gp_sizes();
+    void enqueue_scan_end();
     // export
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();

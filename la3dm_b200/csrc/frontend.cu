@@ -644,7 +644,9 @@ void Map::enqueue_scan(bool frontend_only) {
     enqueue_frontend_bgk();
     if (!frontend_only) {
         enqueue_binning();
-        enqueue_predict();
+        if (hp.method == LA3DM_GP) enqueue_gp();
+        else enqueue_predict();
+        enqueue_scan_end();
     }
 }
 

@@ -499,8 +499,12 @@ void Map::enqueue_predict() {
                                                                    d_lut, d_params, d_args, d_cnt);
     else throw StatusError{LA3DM_ERR_UNSUPPORTED, "block_depth > 4 not supported by the BGK kernel yet"};
     LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    ++launches;
+}
+
+void Map::enqueue_scan_end() {
     k_scan_end<<<1, 1, 0, stream>>>(d_cnt, d_args);
-    launches += 2;
+    ++launches;
 }
 
 }  // namespace la3dm_b200

@@ -1,0 +1,344 @@
+// la3dm_b200 -- GPOctoMap: per-data-block GP training and the fused predict -> Occupancy::update -> prune.
+//
+// Replaces the TRAIN and PREDICT loops of GPOctoMap::insert_pointcloud (src/gpoctomap/gpoctomap.cpp:241-333):
+//   GPRegressor::train   (include/gpoctomap/gpregressor.h:42-51):  K = sf2 (1 + r) exp(-r), r = |sqrt(3)/ell (xi - xj)|,
+//                         K += noise I, LL^T = K, alpha = K^-1 y
+//   GPRegressor::predict (:80-92):  Ks = k(x, xs); m = Ks^T alpha; v = L^-1 Ks; var = sf2 - diag(v^T v)
+//   Occupancy::update    (src/gpoctomap/gpoctree_node.cpp:36-49), applied for EVERY leaf of a test block
+//                         (gpoctomap.cpp:317: no kbar-style guard), prune as in the BGK maps.
+//
+// cond(K + noise I) ~ 1e4 in fp32: a different order of the fp32 operations moves the occupancy probability by more
+// than the 1e-4 parity bound, so both kernels keep the order of the scalar formulation (every dot product is
+// accumulated in ascending index order, products and differences rounded separately); the parallelism is over rows /
+// leaves and over blocks, not inside a dot product.  exp() is evaluated in double and rounded once to fp32.
+#include <cub/cub.cuh>
+
+#include "block_common.cuh"
+
+namespace la3dm_b200 {
+
+namespace {
+
+constexpr int kGpWarps = 4;           // warps per CTA in both kernels
+
+// expf as the reference's host libm computes it: glibc >= 2.27 (the algorithm of ARM's optimized-routines expf,
+// sysdeps/ieee754/flt-32/e_expf.c): x N / ln2 = k + r, exp(x) = 2^(k/N) 2^(r/N) ~ T[k % N] 2^(k/N int part)
+// (C0 r^3 + C1 r^2 + C2 r + 1), all in double, rounded once to float.  Restated here because the GP path amplifies a
+// 1-ulp difference in K by cond(K) ~ 1e4; checked bit for bit against libm on 2e7 arguments.
+__device__ const unsigned long long kExp2fTab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+
+__device__ __forceinline__ float expf_libm(float x) {
+    if (!(x > -87.0f && x < 88.0f)) return (float) exp((double) x);     // outside the fast path of the algorithm
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32,
+                 C2 = 0x1.62e42ff0c52d6p-1 / 32;
+    double z = InvLn2N * (double) x;
+    double kd = z + SHIFT;
+    const unsigned long long ki = (unsigned long long) __double_as_longlong(kd);
+    kd -= SHIFT;
+    const double r = z - kd;
+    const unsigned long long t = kExp2fTab[ki % 32] + (ki << (52 - 5));
+    const double s = __longlong_as_double((long long) t);
+    z = C0 * r + C1;
+    const double r2 = r * r;
+    double y = C2 * r + 1;
+    y = z * r2 + y;
+    y = y * s;
+    return (float) y;
+}
+
+// covMaterniso3 element (gpregressor.h:114-117) on pre-scaled coordinates
+__device__ __forceinline__ float matern3(float ax, float ay, float az, float bx, float by, float bz, float sf2) {
+    const float dx = bx - ax, dy = by - ay, dz = bz - az;
+    const float r = sqrtf(dx * dx + (dy * dy + dz * dz));      // Eigen rowwise().norm() of a 3-vector
+    const float e = expf_libm(-r);
+    return ((1 + r) * e) * sf2;
+}
+
+// floats of factor storage per data block: packed lower triangle of L, then alpha
+__global__ void k_gp_sizes(const unsigned int *__restrict__ db_start, const ScanCounters *__restrict__ c,
+                           unsigned int cap, unsigned long long *sizes) {
+    const unsigned int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= cap) return;
+    unsigned long long s = 0;
+    if (!c->overflow && d < c->n_data_blocks) {
+        const unsigned long long n = db_start[d + 1] - db_start[d];
+        s = n * (n + 1) / 2 + n;
+    }
+    sizes[d] = s;
+}
+
+__global__ void k_gp_check(const unsigned long long *__restrict__ off, const unsigned long long *__restrict__ sizes,
+                           ScanCounters *c, unsigned int cap, unsigned long long store_cap) {
+    if (c->overflow) return;
+    const unsigned int D = min(c->n_data_blocks, cap);
+    const unsigned long long total = D ? off[D - 1] + sizes[D - 1] : 0ull;
+    c->gp_store_needed = total;
+    if (total > store_cap) atomicOr(&c->overflow, OVF_GPSTORE);
+}
+
+// GPRegressor::train, one warp per data block
+__global__ void __launch_bounds__(kGpWarps * 32)
+k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_start,
+           const unsigned long long *__restrict__ off, float *store, const DevParams *__restrict__ Pg,
+           const ScanCounters *__restrict__ c) {
+    if (c->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_w = (gridDim.x * blockDim.x) >> 5;
+    const float sf2 = Pg->sf2, noise = Pg->noise;
+    const unsigned int D = c->n_data_blocks;
+    for (unsigned int d = gw; d < D; d += n_w) {
+        const unsigned int first = db_start[d], n = db_start[d + 1] - first;
+        const float4 *x = pts + first;
+        float *L = store + off[d];                       // L[i][j] at i (i + 1) / 2 + j
+        float *alpha = L + (size_t) n * (n + 1) / 2;
+        // K + noise I, lower triangle (:44-46)
+        for (unsigned int i = 0; i < n; ++i) {
+            const float4 xi = x[i];
+            float *row = L + (size_t) i * (i + 1) / 2;
+            for (unsigned int j = lane; j <= i; j += 32) {
+                const float4 xj = x[j];
+                float k = matern3(xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, sf2);
+                if (i == j) k = k + noise * 1.0f;
+                row[j] = k;
+            }
+        }
+        __syncwarp();
+        // Cholesky (LLT, :47): column by column, a lane per row; each element's sum runs in ascending k
+        for (unsigned int j = 0; j < n; ++j) {
+            const float *rj = L + (size_t) j * (j + 1) / 2;
+            float ljj = 0.f;
+            for (unsigned int i0 = j; i0 < n; i0 += 32) {
+                const unsigned int i = i0 + lane;
+                float s = 0.f;
+                float *ri = nullptr;
+                if (i < n) {
+                    ri = L + (size_t) i * (i + 1) / 2;
+                    s = ri[j];
+                    for (unsigned int k = 0; k < j; ++k) s -= ri[k] * rj[k];
+                }
+                if (i0 == j) {       // lane 0 holds the diagonal element
+                    const float dg = sqrtf(s);
+                    ljj = __shfl_sync(0xffffffffu, dg, 0);
+                    if (lane == 0) s = dg;
+                    else if (i < n) s = s / ljj;
+                } else if (i < n) s = s / ljj;
+                __syncwarp();        // every read of row j's old element is done before the diagonal is overwritten
+                if (i < n) ri[j] = s;
+            }
+            __syncwarp();
+        }
+        // alpha = L^-T (L^-1 y) (:48-49).  Forward: column oriented, every s_i is reduced in ascending k.
+        for (unsigned int i = lane; i < n; i += 32) alpha[i] = x[i].w;
+        __syncwarp();
+        for (unsigned int k = 0; k < n; ++k) {
+            float ak = 0.f;
+            if (lane == 0) { ak = alpha[k] / L[(size_t) k * (k + 1) / 2 + k]; alpha[k] = ak; }
+            ak = __shfl_sync(0xffffffffu, ak, 0);
+            for (unsigned int i = k + 1 + lane; i < n; i += 32) alpha[i] -= L[(size_t) i * (i + 1) / 2 + k] * ak;
+            __syncwarp();
+        }
+        // Backward: s = alpha_i - sum_{k > i, ascending} L_ki alpha_k needs every later alpha first: one lane
+        if (lane == 0) {
+            for (unsigned int ii = n; ii-- > 0;) {
+                float s = alpha[ii];
+                for (unsigned int k = ii + 1; k < n; ++k) s -= L[(size_t) k * (k + 1) / 2 + ii] * alpha[k];
+                alpha[ii] = s / L[(size_t) ii * (ii + 1) / 2 + ii];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Occupancy::update (gpoctree_node.cpp:36-49): a = m_ivar, b = ivar
+__device__ __forceinline__ unsigned char gp_update(float &a, float &b, float m, float var, const DevParams &P,
+                                                   unsigned char old_state) {
+    b = (float) ((double) b + (1.0 / (double) var - (double) P.sf2));
+    a += m / var;
+    if (b < P.min_known_ivar) return LA3DM_UNKNOWN;
+    b = b > P.max_ivar ? P.max_ivar : b;
+    const float p = 1.0f / (1.0f + (float) exp((double) (-P.l * a / P.max_ivar)));
+    (void) old_state;
+    return p > P.occupied_thresh ? LA3DM_OCCUPIED : (p < P.free_thresh ? LA3DM_FREE : LA3DM_UNKNOWN);
+}
+
+struct GpWarpSmem {
+    uint4 rec[kRecMax / 16];
+};
+
+// one warp per test block; a lane owns up to two leaves; for every neighbour with a trained regressor each leaf runs
+// GPRegressor::predict for its centre: ks (n kernel values), m = ks . alpha, forward substitution with L.
+// `scratch` holds ks / v per leaf: [warp][2 arrays][n_max][64 leaves]
+__global__ void __launch_bounds__(kGpWarps * 32)
+k_gp_predict(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__ plan_db,
+             const float4 *__restrict__ pts, const unsigned long long *__restrict__ off,
+             const float *__restrict__ store,
+             const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
+             const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt, float *scratch,
+             unsigned int n_max) {
+    __shared__ GpWarpSmem sm[kGpWarps];
+    __shared__ DevParams Ps;
+    load_params(Ps, Pg);
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GpWarpSmem &S = sm[warp];
+    const unsigned int T = cnt->n_test_blocks;
+    const unsigned int gw = blockIdx.x * kGpWarps + warp, n_w = gridDim.x * kGpWarps;
+    float *ks = scratch + (size_t) gw * 2 * n_max * 64;       // [n_max][64]
+    float *vv = ks + (size_t) n_max * 64;
+    const float sf2 = P.sf2, bs = P.block_size;
+    const float scale = (float) (1.73205 / (double) P.ell);    // gpregressor.h:115
+    const int shard_world = A->shard_world, shard_rank = A->shard_rank;
+    float2 *rab = reinterpret_cast<float2 *>(S.rec);
+    unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + P.st_off;
+    unsigned long long visits = 0, updates = 0, pairs = 0;
+
+    for (unsigned int t = gw; t < T; t += n_w) {
+        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+        const NeighbourPlan pl = plan[t];
+        uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
+        __syncwarp();
+        stage_record(S.rec, grec, pl.is_new != 0, P, lane);
+        const long long key = keys[pl.slot];
+        const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
+                    cz = axis_center(key & 0xFFFFF, bs);
+        __syncwarp();
+        int node[2];
+        resolve_leaves(rst, P, lane, node);
+        float qx[2], qy[2], qz[2], a[2], b[2];
+        unsigned char state[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            qx[s] = qy[s] = qz[s] = a[s] = b[s] = 0.f;
+            state[s] = LA3DM_UNKNOWN;
+            if (node[s] >= 0) {
+                const float2 v = rab[node[s]];
+                a[s] = v.x; b[s] = v.y;
+                state[s] = rst[node[s]];
+                const float3 o = lut[node[s]];
+                // Block::get_loc, then predict()'s  scale * xs  (:84-85 with the stand-in's operand order)
+                qx[s] = scale * (o.x + cx); qy[s] = scale * (o.y + cy); qz[s] = scale * (o.z + cz);
+                ++visits;
+            }
+        }
+        bool touched = false;
+        for (int nb = 0; nb < 7; ++nb) {
+            const unsigned int n = pl.count[nb];
+            if (n == 0) continue;
+            const float4 *x = pts + pl.start[nb];
+            const float *L = store + off[plan_db[(size_t) t * 8 + nb] - 1];
+            const float *alpha = L + (size_t) n * (n + 1) / 2;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (node[s] < 0) continue;
+                const int leaf = lane + 32 * s;
+                pairs += n;
+                float mu = 0.f;
+                for (unsigned int i = 0; i < n; ++i) {
+                    const float4 xi = x[i];
+                    const float k = matern3(xi.x, xi.y, xi.z, qx[s], qy[s], qz[s], sf2);
+                    ks[(size_t) i * 64 + leaf] = k;
+                    mu += k * alpha[i];
+                }
+                float v2 = 0.f;
+                for (unsigned int i = 0; i < n; ++i) {
+                    const float *ri = L + (size_t) i * (i + 1) / 2;
+                    float sacc = ks[(size_t) i * 64 + leaf];
+                    for (unsigned int k = 0; k < i; ++k) sacc -= ri[k] * vv[(size_t) k * 64 + leaf];
+                    const float vi = sacc / ri[i];
+                    vv[(size_t) i * 64 + leaf] = vi;
+                    v2 += vi * vi;
+                }
+                state[s] = gp_update(a[s], b[s], mu, sf2 - v2, P, state[s]) | 0x80;     // gpoctomap.cpp:317
+                touched = true;
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (node[s] >= 0 && touched) {
+                rab[node[s]] = make_float2(a[s], b[s]);
+                rst[node[s]] = state[s];
+                ++updates;
+                any = true;
+            }
+        const bool dirty = __any_sync(0xffffffffu, any) || pl.is_new;
+        __syncwarp();
+        if (dirty) {
+            prune_record(rab, rst, P, lane);
+            for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = S.rec[w];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        visits += __shfl_xor_sync(0xffffffffu, visits, o);
+        updates += __shfl_xor_sync(0xffffffffu, updates, o);
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    }
+    if (lane == 0 && visits) {
+        atomicAdd(&cnt->visits, visits);
+        atomicAdd(&cnt->updates, updates);
+        atomicAdd(&cnt->pairs, pairs);
+    }
+}
+
+// largest data block of the scan (bounds the per-leaf scratch)
+__global__ void k_gp_nmax(const unsigned int *__restrict__ db_start, ScanCounters *c, unsigned int cap,
+                          unsigned int n_max_cap) {
+    if (c->overflow) return;
+    const unsigned int d = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int n = 0;
+    if (d < cap && d < c->n_data_blocks) n = db_start[d + 1] - db_start[d];
+    for (int o = 16; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+    if ((threadIdx.x & 31) == 0 && n) {
+        atomicMax(&c->gp_n_max, n);
+        if (n > n_max_cap) atomicOr(&c->overflow, OVF_GPN);
+    }
+}
+
+}  // namespace
+
+// storage offsets of the regressors and the capacity checks (runs before the map is touched)
+void Map::enqueue_gp_sizes() {
+    if (hp.depth > 3) throw StatusError{LA3DM_ERR_UNSUPPORTED, "GPOctoMap: block_depth > 3 not supported on the GPU yet"};
+    const unsigned int cap = caps.members;     // data blocks <= memberships
+    const int grid = ceil_div(cap, 256);
+    unsigned long long *sizes = gp_sizes.as<unsigned long long>(), *off = gp_off.as<unsigned long long>();
+    k_gp_sizes<<<grid, 256, 0, stream>>>(db_start.as<unsigned int>(), d_cnt, cap, sizes);
+    k_gp_nmax<<<grid, 256, 0, stream>>>(db_start.as<unsigned int>(), d_cnt, cap, caps.gp_n_max);
+    size_t tmp = cub_tmp_bytes;
+    LA3DM_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tmp, sizes, off, (int) cap, stream));
+    k_gp_check<<<1, 1, 0, stream>>>(off, sizes, d_cnt, cap, (unsigned long long) caps.gp_store);
+    launches += 5;
+}
+
+void Map::enqueue_gp() {
+    const unsigned long long *off = gp_off.as<unsigned long long>();
+    const int ctas = num_sms * 4;
+    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    k_gp_train<<<ctas, kGpWarps * 32, 0, stream>>>(pts_sorted.as<float4>(), db_start.as<unsigned int>(), off,
+                                                   gp_store.as<float>(), d_params, d_cnt);
+    k_gp_predict<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), plan_db.as<unsigned int>(),
+                                                        pts_sorted.as<float4>(), off, gp_store.as<float>(),
+                                                        keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
+                                                        d_args, d_cnt, gp_scratch.as<float>(), caps.gp_n_max);
+    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    launches += 2;
+}
+
+size_t scan_temp_bytes(unsigned int items) {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (unsigned long long *) nullptr, (unsigned long long *) nullptr,
+                                  (int) items, nullptr);
+    return tmp;
+}
+
+}  // namespace la3dm_b200
