@@ -464,6 +464,8 @@ void Map::enqueue_binning() {
                                                      test_bits.as<unsigned int>());
     launches += 8 + 2 + (end_bit + 7) / 8;
 
+    // BGKL: per-block training lists (hits + each ray once); the neighbour plan then indexes those
+    if (hp.method == LA3DM_BGKL) enqueue_bgkl_lists(dk.Current(), dv.Current());
     // GP: sizes of the per-data-block regressors -- every capacity check must come before k_plan touches the map
     if (hp.method == LA3DM_GP) enqueue_gp_sizes();
 
@@ -476,7 +478,8 @@ void Map::enqueue_binning() {
                                                    (unsigned int) w_tiles, prescanned, test_id.as<unsigned int>(),
                                                    caps.tests);
     k_plan<<<ceil_div(caps.tests, kThreads), kThreads, 0, stream>>>(
-        test_id.as<unsigned int>(), d_cnt, d_args, d_grid, cell_db.as<unsigned int>(), db_start.as<unsigned int>(),
+        test_id.as<unsigned int>(), d_cnt, d_args, d_grid, cell_db.as<unsigned int>(),
+        hp.method == LA3DM_BGKL ? seg_start.as<unsigned int>() : db_start.as<unsigned int>(),
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
         hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr);
     launches += 3;

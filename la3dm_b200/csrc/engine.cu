@@ -288,6 +288,12 @@ void Map::ensure_workspace() {
     moved |= test_bits.reserve(((size_t) caps.cells / 32 + 2) * 4, stream);
     moved |= test_id.reserve((size_t) caps.tests * 4, stream);
     moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
+    if (hp.method == LA3DM_BGKL) {
+        moved |= ray_of.reserve((size_t) caps.train * 4, stream);
+        moved |= rays.reserve((size_t) caps.points * 2 * sizeof(float4), stream);
+        moved |= segs.reserve((size_t) caps.members * 2 * sizeof(float4), stream);
+        moved |= seg_start.reserve(((size_t) caps.members + 2) * 4, stream);
+    }
     if (hp.method == LA3DM_GP) {
         moved |= gp_sizes.reserve(((size_t) caps.members + 2) * 8, stream);
         moved |= gp_off.reserve(((size_t) caps.members + 2) * 8, stream);
@@ -309,8 +315,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     if (n > 0 && !d_xyz) throw StatusError{LA3DM_ERR_INVALID, "null cloud"};
     if (!(fr > 0)) throw StatusError{LA3DM_ERR_INVALID, "free_res must be > 0"};
     if (ds == 0) throw StatusError{LA3DM_ERR_INVALID, "ds_resolution must not be 0"};
-    if (hp.method != LA3DM_BGK && hp.method != LA3DM_GP)
-        throw StatusError{LA3DM_ERR_UNSUPPORTED, "method not implemented on the GPU yet"};
+    if (hp.method == LA3DM_BGKLV) throw StatusError{LA3DM_ERR_UNSUPPORTED, "method not implemented on the GPU yet"};
     LA3DM_CUDA(cudaSetDevice(device));
     d2h_bytes = 0;
     std::memset(&stats, 0, sizeof(stats));

@@ -52,6 +52,7 @@ struct Map {
     DevBuf test_id, plan;
     DevBuf gp_sizes, gp_off, gp_store, gp_scratch, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
+    DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists
     DevBuf beam_tab;                // sample distances of beam_sample for the current free_resolution
     float beam_tab_fr = 0.f;
     size_t cub_tmp_bytes = 0;
@@ -93,6 +94,9 @@ struct Map {
     // the scan, enqueued on `stream` without host synchronisation (graph-capturable)
     void enqueue_scan(bool frontend_only);
     void enqueue_frontend_bgk();
+    void enqueue_frontend_bgkl();
+    void enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int *sorted_vals);
+    void enqueue_predict_bgkl();
     void enqueue_voxel_grid(int which);
     void enqueue_binning();
     void enqueue_predict();

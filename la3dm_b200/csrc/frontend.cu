@@ -641,10 +641,12 @@ void Map::enqueue_scan(bool frontend_only) {
     launches = 0;
     k_scan_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm);
     ++launches;
-    enqueue_frontend_bgk();
+    if (hp.method == LA3DM_BGKL) enqueue_frontend_bgkl();
+    else enqueue_frontend_bgk();
     if (!frontend_only) {
         enqueue_binning();
         if (hp.method == LA3DM_GP) enqueue_gp();
+        else if (hp.method == LA3DM_BGKL) enqueue_predict_bgkl();
         else enqueue_predict();
         enqueue_scan_end();
     }

@@ -1,0 +1,287 @@
+// la3dm_b200 -- BGKLOctoMap: per-block training lists of points and ray segments, and the fused
+// predict -> Occupancy::update -> prune.
+//
+// Replaces the TRAIN bookkeeping and the PREDICT / PRUNE loops of BGKLOctoMap::insert_pointcloud
+// (src/bgkloctomap/bgkloctomap.cpp:125-182, 190-262):
+//   a block's training set = its hits as degenerate segments + every ray that has a marker in the block, once
+//   (ray_keys de-duplication :145-171);
+//   BGKLInference::predict / point_to_line_dist / covSparseLine (include/bgkloctomap/bgklinference.h:106-141, 183-197):
+//   distance from the voxel centre to the segment, divided by ell AFTER the distance, same sparse kernel;
+//   node.update only if kbar > 0.001f (:231).
+#include "block_common.cuh"
+#include "runs.cuh"
+
+namespace la3dm_b200 {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kSegTile = 32;
+
+// keep flag of sorted membership i: hits always; a marker only if it is the first of its ray in this block (markers of
+// one ray are contiguous in training order, hence contiguous inside the block's sorted range)
+__device__ __forceinline__ bool seg_keep(const unsigned int *keys, const unsigned int *vals, const int *ray_of,
+                                         unsigned int i) {
+    const int rid = ray_of[vals[i]];
+    if (rid < 0 || i == 0) return true;
+    return keys[i] != keys[i - 1] || ray_of[vals[i - 1]] != rid;
+}
+
+__global__ void k_segl_count(const unsigned int *__restrict__ keys, const unsigned int *__restrict__ vals,
+                             const int *__restrict__ ray_of, const ScanCounters *__restrict__ c, unsigned int cap,
+                             unsigned int *tile_sums) {
+    __shared__ unsigned int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const unsigned int n = c->overflow ? 0u : min(c->n_members, cap);
+    unsigned int cnt = 0;
+    for (int k = 0; k < kTileItems; ++k) {
+        const unsigned int i = blockIdx.x * kTile + k * kTileThreads + threadIdx.x;
+        if (i < n && seg_keep(keys, vals, ray_of, i)) ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = s_cnt;
+}
+
+// segs[2 r], segs[2 r + 1] = end points (w of the first = label); seg_start[d] = first segment of data block d
+__global__ void k_segl_place(const unsigned int *__restrict__ keys, const unsigned int *__restrict__ vals,
+                             const int *__restrict__ ray_of, ScanCounters *c, unsigned int cap,
+                             const unsigned int *__restrict__ tile_sums, unsigned int n_tiles,
+                             const float4 *__restrict__ xy, const float4 *__restrict__ rays,
+                             const unsigned int *__restrict__ cell_db, float4 *segs, unsigned int *seg_start) {
+    __shared__ unsigned int smem[66];
+    const unsigned int n = c->overflow ? 0u : min(c->n_members, cap);
+    unsigned int prefix, total;
+    block_tile_prefix(tile_sums, blockIdx.x, n_tiles, smem, prefix, total);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !c->overflow) seg_start[c->n_data_blocks] = total;
+    const unsigned int base = blockIdx.x * kTile + threadIdx.x * kTileItems;
+    unsigned int flags = 0, cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+        const unsigned int i = base + k;
+        if (i < n && seg_keep(keys, vals, ray_of, i)) { flags |= 1u << k; ++cnt; }
+    }
+    unsigned int cta_total;
+    unsigned int pos = prefix + block_exclusive_scan(cnt, smem, cta_total);
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+        if (!(flags & (1u << k))) continue;
+        const unsigned int i = base + k;
+        const unsigned int e = vals[i];
+        const int rid = ray_of[e];
+        if (rid < 0) {                    // a hit: the point twice, label 1 (bgkloctomap.cpp:139-143)
+            const float4 p = xy[e];
+            segs[2 * (size_t) pos] = make_float4(p.x, p.y, p.z, 1.0f);
+            segs[2 * (size_t) pos + 1] = make_float4(p.x, p.y, p.z, 0.0f);
+        } else {                          // the marker's ray, label 0 (:160-166)
+            segs[2 * (size_t) pos] = rays[2 * (size_t) rid];
+            segs[2 * (size_t) pos + 1] = rays[2 * (size_t) rid + 1];
+        }
+        if (i == 0 || keys[i] != keys[i - 1]) seg_start[cell_db[keys[i]] - 1] = pos;
+        ++pos;
+    }
+}
+
+// covSparse element (bgklinference.h:188-191), d already divided by ell; caller guarantees d <= 1
+__device__ __forceinline__ float sparse_kernel(float d, float sf2) {
+    const float t = d * 2.0f * 3.1415926f;
+    float s, c;
+    sincosf(t, &s, &c);
+    float k = (((2.0f + c) * (1.0f - d) / 3.0f) + s / (2.0f * 3.1415926f)) * sf2;
+    return k < 0.0f ? 0.0f : k;
+}
+
+struct UpdateParams {
+    float var_thresh, occupied_thresh, free_thresh;
+};
+
+__device__ __forceinline__ unsigned char bgk_classify(float a, float b, const UpdateParams &P) {
+    const float var = (a * b) / ((a + b) * (a + b) * (a + b + 1.0f));
+    if (var > P.var_thresh) return LA3DM_UNKNOWN;
+    const float p = a / (a + b);
+    return p > P.occupied_thresh ? LA3DM_OCCUPIED : (p < P.free_thresh ? LA3DM_FREE : LA3DM_UNKNOWN);
+}
+
+struct SegSmem {
+    uint4 rec[kRecMax / 16];
+    float4 a[kSegTile];       // p0.xyz, label
+    float4 v[kSegTile];       // p1 - p0, w = |p1 - p0|^2 (fp32, summed left to right) or -1 for a degenerate segment
+    float4 b[kSegTile];       // p1
+};
+
+// point_to_line_dist for one (voxel centre, segment) pair, divided by ell.  c1, c2 are float dot products widened to
+// double upstream; comparing and dividing them in fp32 gives the same results (IEEE division: the double quotient
+// rounded to float equals the float quotient).  point3f::norm(): squares summed left to right, double sqrt, narrowed.
+__device__ __forceinline__ float seg_dist_scaled(float qx, float qy, float qz, const float4 a, const float4 v,
+                                                 const float4 p1, float ell) {
+    const float px = qx - a.x, py = qy - a.y, pz = qz - a.z;
+    float ex = px, ey = py, ez = pz;                       // q - p0
+    if (v.w >= 0.f) {                                      // line_len >= EPSILON
+        const float c1 = px * v.x + py * v.y + pz * v.z;
+        if (c1 > 0) {
+            if (v.w <= c1) { ex = qx - p1.x; ey = qy - p1.y; ez = qz - p1.z; }
+            else {
+                const float b = c1 / v.w;
+                const float nx = a.x + v.x * b, ny = a.y + v.y * b, nz = a.z + v.z * b;
+                ex = qx - nx; ey = qy - ny; ez = qz - nz;
+            }
+        }
+    }
+    const float d = sqrtf(ex * ex + ey * ey + ez * ez);
+    return d / ell;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+k_predict_bgkl(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ segs,
+               const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
+               const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt) {
+    __shared__ SegSmem sm[kWarpsPerCta];
+    __shared__ DevParams Ps;
+    load_params(Ps, Pg);
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SegSmem &S = sm[warp];
+    const unsigned int T = cnt->n_test_blocks;
+    const unsigned int warps_total = gridDim.x * kWarpsPerCta;
+    const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
+    const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
+    const int shard_world = A->shard_world, shard_rank = A->shard_rank;
+    float2 *rab = reinterpret_cast<float2 *>(S.rec);
+    unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + P.st_off;
+    const float reach = 0.5f * (bs - P.resolution) * 1.001f;       // leaf centres lie within this of the block centre
+    const float cull2 = ell * ell * (1.0f + 1e-3f);
+    unsigned long long visits = 0, updates = 0, pairs = 0;
+
+    for (unsigned int t = blockIdx.x * kWarpsPerCta + warp; t < T; t += warps_total) {
+        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+        const NeighbourPlan pl = plan[t];
+        uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
+        __syncwarp();
+        stage_record(S.rec, grec, pl.is_new != 0, P, lane);
+        const long long key = keys[pl.slot];
+        const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
+                    cz = axis_center(key & 0xFFFFF, bs);
+        __syncwarp();
+        int node[2];
+        resolve_leaves(rst, P, lane, node);
+        float qx[2], qy[2], qz[2], a[2], b[2];
+        unsigned char touched[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            qx[s] = qy[s] = qz[s] = a[s] = b[s] = 0.f;
+            touched[s] = 0;
+            if (node[s] >= 0) {
+                const float2 v = rab[node[s]];
+                a[s] = v.x; b[s] = v.y;
+                const float3 o = lut[node[s]];
+                qx[s] = o.x + cx; qy[s] = o.y + cy; qz[s] = o.z + cz;       // Block::get_loc
+                ++visits;
+            }
+        }
+        const bool have1 = __any_sync(0xffffffffu, node[1] >= 0);
+        for (int nb = 0; nb < 7; ++nb) {
+            const unsigned int n = pl.count[nb];
+            if (n == 0) continue;
+            const float4 *src = segs + 2 * (size_t) pl.start[nb];
+            pairs += (unsigned long long) n * ((node[0] >= 0) + (node[1] >= 0));
+            float yb[2] = {0.f, 0.f}, kb[2] = {0.f, 0.f};
+            for (unsigned int base = 0; base < n; base += kSegTile) {
+                const unsigned int m = min((unsigned int) kSegTile, n - base);
+                bool keep = false;
+                float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sv = sa, sb = sa;
+                if ((unsigned int) lane < m) {
+                    sa = src[2 * (size_t) (base + lane)];
+                    sb = src[2 * (size_t) (base + lane) + 1];
+                    sv = make_float4(sb.x - sa.x, sb.y - sa.y, sb.z - sa.z, 0.f);
+                    const float c2 = sv.x * sv.x + sv.y * sv.y + sv.z * sv.z;
+                    const float len = (float) sqrt((double) c2);
+                    sv.w = len < 0.0001f ? -1.0f : c2;                     // EPSILON (bgklinference.h:14)
+                    // cull: distance between the segment's bounding box and the box of the leaf centres
+                    const float gx = fmaxf(fmaxf(fminf(sa.x, sb.x) - (cx + reach), (cx - reach) - fmaxf(sa.x, sb.x)), 0.f);
+                    const float gy = fmaxf(fmaxf(fminf(sa.y, sb.y) - (cy + reach), (cy - reach) - fmaxf(sa.y, sb.y)), 0.f);
+                    const float gz = fmaxf(fmaxf(fminf(sa.z, sb.z) - (cz + reach), (cz - reach) - fmaxf(sa.z, sb.z)), 0.f);
+                    keep = gx * gx + gy * gy + gz * gz < cull2;
+                }
+                unsigned int todo = __ballot_sync(0xffffffffu, keep);
+                if (!todo) continue;
+                __syncwarp();
+                S.a[lane] = sa;
+                S.v[lane] = sv;
+                S.b[lane] = sb;
+                __syncwarp();
+                while (todo) {
+                    const int q = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float4 za = S.a[q], zv = S.v[q], zb = S.b[q];
+                    if (node[0] >= 0) {
+                        const float d = seg_dist_scaled(qx[0], qy[0], qz[0], za, zv, zb, ell);
+                        if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb[0] += k * za.w; kb[0] += k; }
+                    }
+                    if (have1 && node[1] >= 0) {
+                        const float d = seg_dist_scaled(qx[1], qy[1], qz[1], za, zv, zb, ell);
+                        if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb[1] += k * za.w; kb[1] += k; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s)       // Occupancy::update's accumulation, guarded by kbar > 0.001f (:231)
+                if (node[s] >= 0 && kb[s] > 0.001f) { a[s] += yb[s]; b[s] += kb[s] - yb[s]; touched[s] = 1; }
+        }
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (node[s] >= 0 && touched[s]) {
+                rab[node[s]] = make_float2(a[s], b[s]);
+                rst[node[s]] = bgk_classify(a[s], b[s], U) | 0x80;
+                ++updates;
+                any = true;
+            }
+        const bool dirty = __any_sync(0xffffffffu, any) || pl.is_new;
+        __syncwarp();
+        if (dirty) {
+            prune_record(rab, rst, P, lane);
+            for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = S.rec[w];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        visits += __shfl_xor_sync(0xffffffffu, visits, o);
+        updates += __shfl_xor_sync(0xffffffffu, updates, o);
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    }
+    if (lane == 0 && visits) {
+        atomicAdd(&cnt->visits, visits);
+        atomicAdd(&cnt->updates, updates);
+        atomicAdd(&cnt->pairs, pairs);
+    }
+}
+
+}  // namespace
+
+// per-block training lists (after the memberships were sorted by block: engine's binning stage)
+void Map::enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int *sorted_vals) {
+    const int m_tiles = ceil_div(caps.members, kTile);
+    unsigned int *tile_sums = tiles.as<unsigned int>();
+    k_segl_count<<<m_tiles, kTileThreads, 0, stream>>>(sorted_keys, sorted_vals, ray_of.as<int>(), d_cnt, caps.members,
+                                                       tile_sums);
+    k_segl_place<<<m_tiles, kTileThreads, 0, stream>>>(sorted_keys, sorted_vals, ray_of.as<int>(), d_cnt, caps.members,
+                                                       tile_sums, (unsigned int) m_tiles, xy.as<float4>(),
+                                                       rays.as<float4>(), cell_db.as<unsigned int>(), segs.as<float4>(),
+                                                       seg_start.as<unsigned int>());
+    launches += 2;
+}
+
+void Map::enqueue_predict_bgkl() {
+    if (hp.depth > 3) throw StatusError{LA3DM_ERR_UNSUPPORTED, "BGKLOctoMap: block_depth > 3 not supported on the GPU yet"};
+    const int ctas = num_sms * 3;
+    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    k_predict_bgkl<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), segs.as<float4>(),
+                                                           keys.as<long long>(), pool.as<unsigned char>(), d_lut,
+                                                           d_params, d_args, d_cnt);
+    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    ++launches;
+}
+
+}  // namespace la3dm_b200
