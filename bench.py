@@ -241,6 +241,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line the driver parses
         dist.init_process_group("nccl", device_id=dev)
 
     n = a.warmup + a.steps

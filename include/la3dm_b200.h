@@ -147,6 +147,13 @@ int la3dm_training_data(la3dm_map *map, const float *xyz, size_t n, size_t strid
                         float ds_resolution, float free_res, float max_range, float *out, size_t capacity,
                         size_t *n_out);
 
+/* BGKL / BGKLV only: the ray segments and the ray index of every training entry produced by the LAST
+ * la3dm_training_data / la3dm_insert_pointcloud call (get_training_data's `rays` and `ray_idx` outputs,
+ * src/bgkloctomap/bgkloctomap.cpp:285-344, src/bgklvoctomap/bgklvoctomap.cpp:303-423).  rays: 6 floats per ray
+ * (x0 y0 z0 x1 y1 z1); ray_idx: one int32 per training entry (-1 for a hit).  Either output may be NULL. */
+int la3dm_training_rays(la3dm_map *map, float *rays, size_t ray_capacity, size_t *n_rays, int32_t *ray_idx,
+                        size_t idx_capacity);
+
 int la3dm_last_stats(const la3dm_map *map, la3dm_scan_stats *out);
 
 /* ---- read side ----------------------------------------------------------------------------------------------- */

@@ -54,6 +54,7 @@ SYMBOLS = {
                                                  C.c_float]),
     "la3dm_training_data": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float, C.c_float, _P,
                                       C.c_size_t, C.POINTER(C.c_size_t)]),
+    "la3dm_training_rays": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_size_t]),
     "la3dm_last_stats": (C.c_int, [_P, C.POINTER(ScanStats)]),
     "la3dm_num_blocks": (C.c_int64, [_P]),
     "la3dm_nodes_per_block": (C.c_int32, [_P]),

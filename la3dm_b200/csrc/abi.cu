@@ -128,6 +128,35 @@ int la3dm_training_data(la3dm_map *map, const float *xyz, size_t n, size_t strid
     });
 }
 
+int la3dm_training_rays(la3dm_map *map, float *rays, size_t ray_capacity, size_t *n_rays, int32_t *ray_idx,
+                        size_t idx_capacity) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] {
+        Map &m = map->m;
+        if (m.hp.method != LA3DM_BGKL && m.hp.method != LA3DM_BGKLV)
+            throw la3dm_b200::StatusError{LA3DM_ERR_UNSUPPORTED, "training_rays: BGKL / BGKLV only"};
+        LA3DM_CUDA(cudaSetDevice(m.device));
+        LA3DM_CUDA(cudaStreamSynchronize(m.stream));
+        const size_t nr = m.hp.method == LA3DM_BGKL ? (size_t) m.h_cnt->n_hits : (size_t) m.h_cnt->n_frees;
+        const size_t nt = (size_t) m.h_cnt->n_train;
+        if (n_rays) *n_rays = nr;
+        if (rays && nr) {
+            if (ray_capacity < nr) throw la3dm_b200::StatusError{LA3DM_ERR_INVALID, "training_rays: capacity too small"};
+            std::vector<float4> h(2 * nr);
+            LA3DM_CUDA(cudaMemcpy(h.data(), m.rays.p, 2 * nr * sizeof(float4), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < nr; ++i) {
+                float *o = rays + 6 * i;
+                o[0] = h[2 * i].x; o[1] = h[2 * i].y; o[2] = h[2 * i].z;
+                o[3] = h[2 * i + 1].x; o[4] = h[2 * i + 1].y; o[5] = h[2 * i + 1].z;
+            }
+        }
+        if (ray_idx && nt) {
+            if (idx_capacity < nt) throw la3dm_b200::StatusError{LA3DM_ERR_INVALID, "training_rays: capacity too small"};
+            LA3DM_CUDA(cudaMemcpy(ray_idx, m.ray_of.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        }
+    });
+}
+
 int la3dm_last_stats(const la3dm_map *map, la3dm_scan_stats *out) {
     if (!map || !out) return LA3DM_ERR_INVALID;
     *out = map->m.stats;

@@ -429,6 +429,13 @@ void Map::ensure_pool(size_t blocks) {
     }
 }
 
+// the float-stepped block grid of the scan from the bounding box of the training set (d_mm + 12)
+void Map::enqueue_block_grid() {
+    LA3DM_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(GridDesc), stream));
+    k_grid<<<1, 32, 0, stream>>>(d_mm + 12, d_params, d_grid, d_cnt, caps.cells);
+    ++launches;
+}
+
 // Input: xy[0..n_train) and the counters on the device.
 // Output: pts_sorted, db_id/db_start, test_id, plan[] (slot, is_new, 7 ranges); counters on the device.
 void Map::enqueue_binning() {
@@ -438,11 +445,10 @@ void Map::enqueue_binning() {
 
     // bbox of the training set and the float-stepped block grid; dense per-cell tables start empty
     // (the bounding box mm was accumulated by the front-end kernels that wrote xy)
-    LA3DM_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(GridDesc), stream));
+    enqueue_block_grid();
     LA3DM_CUDA(cudaMemsetAsync(cell_db.p, 0, (size_t) caps.cells * 4, stream));
     const unsigned int n_words = (caps.cells + 31) / 32;
     LA3DM_CUDA(cudaMemsetAsync(test_bits.p, 0, (size_t) n_words * 4, stream));
-    k_grid<<<1, 32, 0, stream>>>(mm, d_params, d_grid, d_cnt, caps.cells);
 
     // memberships -> sort by cell
     const int t_tiles = ceil_div(caps.train, kTile);
@@ -462,7 +468,7 @@ void Map::enqueue_binning() {
                                                      pts_sorted.as<float4>(), db_id.as<unsigned int>(),
                                                      db_start.as<unsigned int>(), cell_db.as<unsigned int>(),
                                                      test_bits.as<unsigned int>());
-    launches += 8 + 2 + (end_bit + 7) / 8;
+    launches += 7 + 2 + (end_bit + 7) / 8;
 
     // BGKL: per-block training lists (hits + each ray once); the neighbour plan then indexes those
     if (hp.method == LA3DM_BGKL) enqueue_bgkl_lists(dk.Current(), dv.Current());

@@ -139,15 +139,17 @@ struct Caps {
     unsigned int vg_cells;  // linear voxel-grid index space (sets the radix-sort bit count)
     unsigned int gp_store;  // GP: floats of factor storage (packed L + alpha per data block)
     unsigned int gp_n_max;  // GP: largest data block the per-leaf scratch is sized for
+    unsigned int lv_active; // BGKLV: voxels that have training data in their query box
     bool operator==(const Caps &o) const {
         return points == o.points && raw == o.raw && train == o.train && members == o.members && cells == o.cells &&
-               tests == o.tests && vg_cells == o.vg_cells && gp_store == o.gp_store && gp_n_max == o.gp_n_max;
+               tests == o.tests && vg_cells == o.vg_cells && gp_store == o.gp_store && gp_n_max == o.gp_n_max &&
+               lv_active == o.lv_active;
     }
 };
 
 enum : unsigned int {
     OVF_RAW = 1u, OVF_MEMBERS = 2u, OVF_CELLS = 4u, OVF_TESTS = 8u, OVF_EXTENT = 16u, OVF_POOL = 32u, OVF_VGCELLS = 64u,
-    OVF_GPSTORE = 128u, OVF_GPN = 256u
+    OVF_GPSTORE = 128u, OVF_GPN = 256u, OVF_LVACTIVE = 512u
 };
 
 // counters the host reads back once per scan (pinned mirror)
@@ -172,6 +174,8 @@ struct ScanCounters {
     unsigned int n_blocks;       // blocks in the map after the scan
     unsigned int vg_cells_needed;
     unsigned int gp_n_max;       // GP: largest data block of the scan
+    unsigned int lv_active;      // BGKLV: active voxels of the scan
+    unsigned int pad_;
     unsigned long long gp_store_needed;
 };
 

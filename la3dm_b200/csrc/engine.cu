@@ -99,6 +99,16 @@ __global__ void k_leaf_fill(const unsigned char *__restrict__ pool, const long l
                     // gpoctree_node.cpp:31-34, gpoctree_node.h:60
                     L.prob = 1.0f / (1.0f + (float) exp((double) (-P.l * v.x / P.max_ivar)));
                     L.var = 1.0f / v.y;
+                } else if (P.method == LA3DM_BGKLV) {
+                    // bgklvoctree_node.cpp:29-62
+                    const float W = (v.x + v.y < P.min_W) ? P.min_W : v.x + v.y;
+                    float pr;
+                    if (v.x > v.y) pr = (float) ((double) (v.x / (W - v.y)) + (double) (W - v.x - v.y) * 0.5 / (double) (W - v.y));
+                    else pr = (float) (0.5 * (double) (W - v.y - v.x) / (double) (W - v.x));
+                    L.prob = pr;
+                    L.var = (float) ((double) (v.x / W) * pow((double) (1 - pr), 2.0) +
+                                     (double) ((W - v.x - v.y) / W) * pow(0.5 - (double) pr, 2.0) +
+                                     (double) (v.y / W) * pow((double) pr, 2.0));
                 } else {
                     L.prob = v.x / (v.x + v.y);                                        // bgkoctree_node.cpp:27-29
                     L.var = (v.x * v.y) / ((v.x + v.y) * (v.x + v.y) * (v.x + v.y + 1.0f));   // bgkoctree_node.h:60
@@ -125,6 +135,8 @@ unsigned int grow_to(unsigned int need, unsigned int floor_) {
 
 size_t radix_sort_temp_bytes(unsigned int items);   // frontend.cu
 size_t scan_temp_bytes(unsigned int items);         // predict_gp.cu
+size_t lv_ray_info_bytes();                         // frontend_lv.cu
+size_t lv_qgrid_bytes();                            // predict_lv.cu
 
 Map::~Map() {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -235,6 +247,7 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     caps.vg_cells = 1u << 20;
     caps.gp_store = method == LA3DM_GP ? (1u << 22) : 0;
     caps.gp_n_max = method == LA3DM_GP ? 160 : 0;
+    caps.lv_active = method == LA3DM_BGKLV ? (1u << 18) : 0;
     ensure_pool(4096 + caps.tests);
     ensure_workspace();
     LA3DM_CUDA(cudaStreamSynchronize(stream));
@@ -288,7 +301,16 @@ void Map::ensure_workspace() {
     moved |= test_bits.reserve(((size_t) caps.cells / 32 + 2) * 4, stream);
     moved |= test_id.reserve((size_t) caps.tests * 4, stream);
     moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
-    if (hp.method == LA3DM_BGKL) {
+    if (hp.method == LA3DM_BGKLV) {
+        moved |= lv_range.reserve((size_t) caps.points * 8, stream);
+        moved |= lv_info.reserve((size_t) caps.points * lv_ray_info_bytes(), stream);
+        moved |= ray_first.reserve((size_t) caps.points * 4, stream);
+        moved |= lv_qgrid.reserve(lv_qgrid_bytes(), stream);
+        moved |= lv_active.reserve((size_t) caps.lv_active * 8, stream);
+        moved |= lv_blk_slot.reserve((size_t) caps.tests * 4, stream);
+        moved |= lv_blk_flags.reserve((size_t) caps.tests, stream);
+    }
+    if (hp.method == LA3DM_BGKL || hp.method == LA3DM_BGKLV) {
         moved |= ray_of.reserve((size_t) caps.train * 4, stream);
         moved |= rays.reserve((size_t) caps.points * 2 * sizeof(float4), stream);
         moved |= segs.reserve((size_t) caps.members * 2 * sizeof(float4), stream);
@@ -315,7 +337,8 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     if (n > 0 && !d_xyz) throw StatusError{LA3DM_ERR_INVALID, "null cloud"};
     if (!(fr > 0)) throw StatusError{LA3DM_ERR_INVALID, "free_res must be > 0"};
     if (ds == 0) throw StatusError{LA3DM_ERR_INVALID, "ds_resolution must not be 0"};
-    if (hp.method == LA3DM_BGKLV) throw StatusError{LA3DM_ERR_UNSUPPORTED, "method not implemented on the GPU yet"};
+    // BGKLV clamps the downsampling resolution to the map resolution (src/bgklvoctomap/bgklvoctomap.cpp:102-104)
+    if (hp.method == LA3DM_BGKLV && ds > hp.resolution) ds = hp.resolution;
     LA3DM_CUDA(cudaSetDevice(device));
     d2h_bytes = 0;
     std::memset(&stats, 0, sizeof(stats));
@@ -388,6 +411,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (ovf & OVF_GPSTORE)
             caps.gp_store = grow_to((unsigned int) std::min<unsigned long long>(h_cnt->gp_store_needed, 0x60000000ull), 1u << 22);
         if (ovf & OVF_GPN) caps.gp_n_max = grow_to(h_cnt->gp_n_max, 160);
+        if (ovf & OVF_LVACTIVE) caps.lv_active = grow_to(h_cnt->lv_active, 1u << 18);
         caps.train = caps.points + caps.raw;
         if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }

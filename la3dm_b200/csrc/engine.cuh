@@ -53,6 +53,7 @@ struct Map {
     DevBuf gp_sizes, gp_off, gp_store, gp_scratch, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
     DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists
+    DevBuf lv_range, lv_info, ray_first, lv_qgrid, lv_active, lv_blk_slot, lv_blk_flags;   // BGKLVOctoMap
     DevBuf beam_tab;                // sample distances of beam_sample for the current free_resolution
     float beam_tab_fr = 0.f;
     size_t cub_tmp_bytes = 0;
@@ -97,6 +98,9 @@ struct Map {
     void enqueue_frontend_bgkl();
     void enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int *sorted_vals);
     void enqueue_predict_bgkl();
+    void enqueue_frontend_lv();
+    void enqueue_lv();
+    void enqueue_block_grid();
     void enqueue_voxel_grid(int which);
     void enqueue_binning();
     void enqueue_predict();

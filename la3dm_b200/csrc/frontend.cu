@@ -642,8 +642,12 @@ void Map::enqueue_scan(bool frontend_only) {
     k_scan_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm);
     ++launches;
     if (hp.method == LA3DM_BGKL) enqueue_frontend_bgkl();
+    else if (hp.method == LA3DM_BGKLV) enqueue_frontend_lv();
     else enqueue_frontend_bgk();
-    if (!frontend_only) {
+    if (!frontend_only && hp.method == LA3DM_BGKLV) {
+        enqueue_lv();
+        enqueue_scan_end();
+    } else if (!frontend_only) {
         enqueue_binning();
         if (hp.method == LA3DM_GP) enqueue_gp();
         else if (hp.method == LA3DM_BGKL) enqueue_predict_bgkl();

@@ -101,8 +101,10 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__
 
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
-    for (unsigned int t = blockIdx.x * kWarpsPerCta + warp; t < T; t += warps_total) {
-        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+    // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over its warps
+    for (unsigned int u = blockIdx.x * kWarpsPerCta + warp;; u += warps_total) {
+        const unsigned int t = u * (unsigned int) shard_world + (unsigned int) shard_rank;
+        if (t >= T) break;
         // ---- plan: lanes 0..6 hold start/count of one neighbour each
         const NeighbourPlan *pl = plan + t;
         const unsigned int slot = pl->slot, is_new = pl->is_new;
@@ -361,8 +363,10 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     const int shard_world = A->shard_world, shard_rank = A->shard_rank;
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
-    for (unsigned int t = blockIdx.x * kWarpsPerCta + warp; t < T; t += warps_total) {
-        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+    // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over its warps
+    for (unsigned int u = blockIdx.x * kWarpsPerCta + warp;; u += warps_total) {
+        const unsigned int t = u * (unsigned int) shard_world + (unsigned int) shard_rank;
+        if (t >= T) break;
         const NeighbourPlan pl = plan[t];
         unsigned char *rec = pool + (size_t) pl.slot * (size_t) P.rec_bytes;
         float2 *bab = reinterpret_cast<float2 *>(rec);

@@ -155,8 +155,10 @@ k_predict_bgkl(const NeighbourPlan *__restrict__ plan, const float4 *__restrict_
     const float cull2 = ell * ell * (1.0f + 1e-3f);
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
-    for (unsigned int t = blockIdx.x * kWarpsPerCta + warp; t < T; t += warps_total) {
-        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+    // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over its warps
+    for (unsigned int u = blockIdx.x * kWarpsPerCta + warp;; u += warps_total) {
+        const unsigned int t = u * (unsigned int) shard_world + (unsigned int) shard_rank;
+        if (t >= T) break;
         const NeighbourPlan pl = plan[t];
         uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
         __syncwarp();

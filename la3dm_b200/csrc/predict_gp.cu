@@ -202,8 +202,9 @@ k_gp_predict(const NeighbourPlan *__restrict__ plan, const unsigned int *__restr
     unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + P.st_off;
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
-    for (unsigned int t = gw; t < T; t += n_w) {
-        if (shard_world > 1 && (int) (t % (unsigned int) shard_world) != shard_rank) continue;
+    for (unsigned int u = gw;; u += n_w) {
+        const unsigned int t = u * (unsigned int) shard_world + (unsigned int) shard_rank;
+        if (t >= T) break;
         const NeighbourPlan pl = plan[t];
         uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
         __syncwarp();

@@ -81,6 +81,16 @@ class _OctoMapBase:
             self._check(self._lib.la3dm_training_data(*args, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def training_rays(self):
+        """BGKL / BGKLV: (rays [R,6], ray_idx [N]) of the last training_data() / insert_pointcloud() call."""
+        n = C.c_size_t(0)
+        self._check(self._lib.la3dm_training_rays(self._h, None, 0, C.byref(n), None, 0))
+        rays = np.zeros((n.value, 6), np.float32)
+        idx = np.zeros(int(self.last_stats()["n_train"]), np.int32)
+        self._check(self._lib.la3dm_training_rays(self._h, rays.ctypes.data, n.value, C.byref(n), idx.ctypes.data,
+                                                  idx.shape[0]))
+        return rays, idx
+
     def last_stats(self):
         s = ScanStats()
         self._check(self._lib.la3dm_last_stats(self._h, C.byref(s)))
