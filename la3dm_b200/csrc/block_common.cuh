@@ -7,6 +7,15 @@ namespace la3dm_b200 {
 
 constexpr int kRecMax = 672;          // bytes of a depth-3 record: 73 * 8 + 73 -> 16-byte multiple
 
+// default record in shared memory: every node = (prior_A, prior_B | 0, min_ivar), UNKNOWN, !classified
+// (bgkoctree_node.h:34 / gpoctree_node.h:34); the spare bytes behind the states are zero except the leaf count
+__device__ __forceinline__ void stage_default_record(uint4 *srec, const DevParams &P, int lane) {
+    float2 *rab = reinterpret_cast<float2 *>(srec);
+    unsigned char *rb = reinterpret_cast<unsigned char *>(srec);
+    for (int n = lane; n < P.nodes; n += 32) { rab[n] = make_float2(P.def_a, P.def_b); rb[P.st_off + n] = LA3DM_UNKNOWN; }
+    for (int n = P.st_off + P.nodes + lane; n < P.rec_bytes; n += 32) rb[n] = n == P.st_off + P.nodes ? (unsigned char) P.finest : 0;
+}
+
 // record -> shared memory (a fresh Block gets the default node everywhere: bgkoctree_node.h:34 / gpoctree_node.h:34)
 __device__ __forceinline__ void stage_record(uint4 *srec, const uint4 *grec, bool is_new, const DevParams &P, int lane) {
     float2 *rab = reinterpret_cast<float2 *>(srec);
