@@ -350,6 +350,15 @@ def run_ours(a):
         k_bytes = float(np.mean([BYTES_PER_VISIT * vis[s] / world + BYTES_PER_MEMBER * st_d[s]["n_train"] +
                                  BYTES_PER_TEST_BLOCK * st_d[s]["n_test_blocks"] / world for s in timed]))
         k_flop = float(np.mean([FLOP_PER_PAIR * pairs[s] / world for s in timed]))
+        # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel (profiles/), if present
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "predict_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("points") == a.points and tj.get("extent") == a.extent:
+                traffic = tj["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
         ach_gbs = k_bytes / (k_ms * 1e-3) / 1e9
         ach_tf = k_flop / (k_ms * 1e-3) / 1e12
         line = {
@@ -371,7 +380,7 @@ def run_ours(a):
             "collectives_per_step": st_d[timed[0]]["collectives"],
             "roofline": {"kernel": "k_predict_bgk (fused predict + Occupancy::update + prune)", "bound": "hbm",
                          "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (1e3 * T / a.steps), "algorithmic_bytes": k_bytes,
                          "note": "the pair loop is fp32-pipe bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": float(fp32.value), "unit": "TFLOP/s",

@@ -269,6 +269,14 @@ void Map::ensure_beam_table(float fr) {
     beam_tab_fr = fr;
 }
 
+// timing events around the predict kernels: an event-record node when the scan is being captured into a graph
+void Map::record_event(cudaEvent_t ev) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    LA3DM_CUDA(cudaStreamIsCapturing(stream, &st));
+    if (st == cudaStreamCaptureStatusActive) LA3DM_CUDA(cudaEventRecordWithFlags(ev, stream, cudaEventRecordExternal));
+    else LA3DM_CUDA(cudaEventRecord(ev, stream));
+}
+
 void Map::invalidate_graph() {
     if (graph_exec) {
         cudaStreamSynchronize(stream);

@@ -90,6 +90,7 @@ struct Map {
     void ensure_workspace();
     void ensure_beam_table(float fr);
     void invalidate_graph();
+    void record_event(cudaEvent_t ev);   // inside or outside of a stream capture
     void insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
                        float max_range, bool frontend_only);
     // the scan, enqueued on `stream` without host synchronisation (graph-capturable)

@@ -504,7 +504,7 @@ __global__ void k_scan_end(ScanCounters *c, const ScanArgs *__restrict__ A) {
 void Map::enqueue_predict() {
     if (hp.method != LA3DM_BGK) throw StatusError{LA3DM_ERR_UNSUPPORTED, "predict: method not implemented yet"};
     const int ctas = num_sms * 4;
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    record_event(ev_p0);
     if (hp.depth <= 3)
         k_predict_bgk<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
                                                               keys.as<long long>(), pool.as<unsigned char>(), d_lut,
@@ -514,7 +514,7 @@ void Map::enqueue_predict() {
                                                                    keys.as<long long>(), pool.as<unsigned char>(),
                                                                    d_lut, d_params, d_args, d_cnt);
     else throw StatusError{LA3DM_ERR_UNSUPPORTED, "block_depth > 4 not supported by the BGK kernel yet"};
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    record_event(ev_p1);
     ++launches;
 }
 

@@ -278,11 +278,11 @@ void Map::enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int
 void Map::enqueue_predict_bgkl() {
     if (hp.depth > 3) throw StatusError{LA3DM_ERR_UNSUPPORTED, "BGKLOctoMap: block_depth > 3 not supported on the GPU yet"};
     const int ctas = num_sms * 3;
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    record_event(ev_p0);
     k_predict_bgkl<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), segs.as<float4>(),
                                                            keys.as<long long>(), pool.as<unsigned char>(), d_lut,
                                                            d_params, d_args, d_cnt);
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    record_event(ev_p1);
     ++launches;
 }
 

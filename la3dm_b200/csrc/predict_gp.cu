@@ -324,14 +324,14 @@ void Map::enqueue_gp_sizes() {
 void Map::enqueue_gp() {
     const unsigned long long *off = gp_off.as<unsigned long long>();
     const int ctas = num_sms * 4;
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    record_event(ev_p0);
     k_gp_train<<<ctas, kGpWarps * 32, 0, stream>>>(pts_sorted.as<float4>(), db_start.as<unsigned int>(), off,
                                                    gp_store.as<float>(), d_params, d_cnt);
     k_gp_predict<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), plan_db.as<unsigned int>(),
                                                         pts_sorted.as<float4>(), off, gp_store.as<float>(),
                                                         keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
                                                         d_args, d_cnt, gp_scratch.as<float>(), caps.gp_n_max);
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    record_event(ev_p1);
     launches += 2;
 }
 

@@ -486,14 +486,14 @@ void Map::enqueue_lv() {
     k_lv_init_new<<<wide, kThreads, 0, stream>>>(d_grid, d_cnt, d_params, lv_blk_slot.as<unsigned int>(),
                                                  lv_blk_flags.as<unsigned char>(), pool.as<unsigned char>(),
                                                  caps.lv_active);
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p0, stream, cudaEventRecordExternal));
+    record_event(ev_p0);
     k_lv_predict<<<wide, kThreads, 0, stream>>>(lv_active.as<uint2>(), d_grid, qg, d_cnt, d_params, d_lut,
                                                 lv_blk_slot.as<unsigned int>(), lv_blk_flags.as<unsigned char>(),
                                                 pool.as<unsigned char>(), d_xy, ray_of.as<int>(), rays.as<float4>(),
                                                 ray_first.as<unsigned int>(), dv.Current(),
                                                 db_start.as<unsigned int>(), cell_db.as<unsigned int>(),
                                                 caps.lv_active);
-    LA3DM_CUDA(cudaEventRecordWithFlags(ev_p1, stream, cudaEventRecordExternal));
+    record_event(ev_p1);
     k_lv_prune<<<num_sms * 2, kThreads, 0, stream>>>(d_grid, d_cnt, d_params, lv_blk_slot.as<unsigned int>(),
                                                     lv_blk_flags.as<unsigned char>(), pool.as<unsigned char>());
     k_lv_finish<<<1, 1, 0, stream>>>(d_cnt);
