@@ -182,7 +182,9 @@ void la3dm_get_extended_block(const la3dm_map *map, int64_t key, int64_t out7[7]
 /* Every rank holds a full replica of the map and runs the (cheap) front-end redundantly; rank r predicts the test
  * blocks t with t % world == r.  After insert, each rank packs the node states of ITS blocks; the caller all-gathers
  * the packed buffers (NCCL, e.g. torch.distributed.all_gather_into_tensor on device tensors) and every rank unpacks
- * the peers' rows, so that all replicas are identical again.  Buffers are DEVICE pointers. */
+ * the peers' rows, so that all replicas are identical again.  Buffers are DEVICE pointers.  pack / unpack only ENQUEUE
+ * their kernel on la3dm_stream(map) (no host synchronisation): issue the collective stream-ordered on that stream (or
+ * order it with events), and synchronise the stream before reading the map from another stream. */
 int la3dm_set_shard(la3dm_map *map, int rank, int world);
 int64_t la3dm_shard_row_bytes(const la3dm_map *map);             /* bytes per packed block                 */
 int64_t la3dm_shard_rows(const la3dm_map *map);                  /* rows per rank = ceil(T / world)         */

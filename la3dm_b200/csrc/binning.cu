@@ -18,36 +18,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr unsigned int kPad = 0xFFFFFFFFu;
 
-// ---- bbox of the training set (src/bgkoctomap/bgkoctomap.cpp:464-484) ----------------------------------------------
-__global__ void k_bbox_minmax(const float4 *__restrict__ xy, const ScanCounters *__restrict__ c, unsigned int *mm) {
-    if (c->overflow) return;
-    const unsigned int n = c->n_train;
-    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
-    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    bool any = false;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 p = xy[i];
-        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
-        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
-        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
-        any = true;
-    }
-    if (!__any_sync(0xffffffffu, any)) return;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
-        }
-    }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMin(&mm[a], float_flip(mn[a]));
-            atomicMax(&mm[3 + a], float_flip(mx[a]));
-        }
-    }
-}
+// (the bounding box of the training set, src/bgkoctomap/bgkoctomap.cpp:464-484, is accumulated by the front-end kernels
+// that write xy: k_hit_fill, k_vg_centroid<1>, k_vg_long<1>)
 
 // ---- block grid of the scan (get_blocks_in_bbox, :486-495); *g was zeroed by a memset ------------------------------
 __global__ void k_grid(const unsigned int *__restrict__ mm, const DevParams *__restrict__ P, GridDesc *g,
@@ -440,10 +412,9 @@ void Map::enqueue_block_grid() {
 // Output: pts_sorted, db_id/db_start, test_id, plan[] (slot, is_new, 7 ranges); counters on the device.
 void Map::enqueue_binning() {
     const float4 *d_xy = xy.as<float4>();
-    unsigned int *mm = d_mm + 12;
     unsigned int *tile_sums = tiles.as<unsigned int>();
 
-    // bbox of the training set and the float-stepped block grid; dense per-cell tables start empty
+    // the float-stepped block grid; dense per-cell tables start empty
     // (the bounding box mm was accumulated by the front-end kernels that wrote xy)
     enqueue_block_grid();
     LA3DM_CUDA(cudaMemsetAsync(cell_db.p, 0, (size_t) caps.cells * 4, stream));

@@ -40,7 +40,6 @@ struct Map {
 
     // ---- per-scan workspace, sized by `caps`
     Caps caps{};                    // logical capacities the scan kernels check against
-    Caps alloc{};                   // what the buffers can hold (>= caps)
     DevBuf cloud;                   // uploaded scan (host entry point)
     DevBuf sort_keys[2], sort_vals[2], run_start, cub_tmp, tiles, long_list, long_flags, hit_cnt;
     DevBuf hits_ds;                 // float4 voxel-grid output of the cloud

@@ -53,8 +53,9 @@ static int shard_copy(la3dm_map *map, void *rows, int pack) {
     la3dm_b200::k_shard_copy<<<la3dm_b200::ceil_div((long long) total * 32, 256), 256, 0, m.stream>>>(
         m.plan.as<la3dm_b200::NeighbourPlan>(), &m.d_cnt->n_test_blocks, m.pool.as<unsigned char>(), m.hp.rec_bytes,
         static_cast<unsigned char *>(rows), rpr, m.shard_world, m.shard_rank, pack);
-    if (cudaStreamSynchronize(m.stream) != cudaSuccess) {
-        m.last_error = cudaGetErrorString(cudaGetLastError());
+    // stream-ordered on la3dm_stream(map): the caller orders its collective after / before these kernels on that stream
+    if (cudaGetLastError() != cudaSuccess) {
+        m.last_error = "shard copy kernel launch failed";
         return LA3DM_ERR_CUDA;
     }
     return LA3DM_OK;

@@ -136,6 +136,15 @@ class _OctoMapBase:
                                                       C.byref(n)))
         return keys, nodes
 
+    def blocks_keys_only(self):
+        """(keys [B] sorted, None): block keys without the node arrays (for maps too large to mirror on the host)."""
+        n = C.c_size_t(0)
+        self._check(self._lib.la3dm_export_blocks(self._h, None, None, 0, C.byref(n)))
+        keys = np.zeros(n.value, np.int64)
+        if n.value:
+            self._check(self._lib.la3dm_export_blocks(self._h, keys.ctypes.data, None, n.value, C.byref(n)))
+        return keys, None
+
     def get_bbox(self):
         mn = np.zeros(3, np.float32)
         mx = np.zeros(3, np.float32)
