@@ -115,6 +115,8 @@ typedef struct la3dm_scan_stats {
     float predict_ms;        /* device time of the fused predict/update/prune kernel alone           */
     int64_t h2d_bytes;       /* bytes copied host -> device by this call (the cloud)                  */
     int64_t d2h_bytes;       /* bytes copied device -> host by this call (counters)                   */
+    int32_t replays;         /* times this call re-ran the scan after growing a workspace (map untouched) */
+    int32_t graph_captures;  /* 1 if this call (re)captured the scan's CUDA graph                     */
 } la3dm_scan_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------ */

@@ -38,7 +38,8 @@ class ScanStats(C.Structure):
                 ("n_test_blocks", C.c_int64), ("voxel_visits", C.c_int64), ("voxel_updates", C.c_int64),
                 ("kernel_pairs", C.c_int64), ("n_blocks_total", C.c_int64), ("new_blocks", C.c_int64),
                 ("kernel_launches", C.c_int32), ("grid_irregular", C.c_int32), ("device_ms", C.c_float),
-                ("predict_ms", C.c_float), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("predict_ms", C.c_float), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("replays", C.c_int32), ("graph_captures", C.c_int32)]
 
 
 # every symbol include/la3dm_b200.h declares: name -> (restype, argtypes)

@@ -381,7 +381,9 @@ inline int bits_for(unsigned int n) {
 // capacity for `blocks` blocks in the pool and a hash table at <= 50 % load (host side, between scans)
 void Map::ensure_pool(size_t blocks) {
     if (blocks > pool_cap) {
-        const size_t want = blocks + blocks / 2 + 1024;
+        // grow-only, doubling (a move copies the pool and invalidates the captured graph); first allocation ~1 GB
+        const size_t first = ((size_t) 1 << 30) / (size_t) hp.rec_bytes;
+        const size_t want = std::max(2 * blocks + 1024, first);
         keys.grow_keep(want * sizeof(long long), stream);
         pool.grow_keep(want * (size_t) hp.rec_bytes, stream);
         pool_cap = want;

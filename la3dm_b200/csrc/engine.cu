@@ -353,6 +353,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     stats.n_points = (int64_t) n;
     last_T = 0;
 
+    int call_replays = 0, call_captures = 0;
     for (int attempt = 0;; ++attempt) {
         if (attempt > 12) throw StatusError{LA3DM_ERR_NOMEM, "scan workspace did not settle"};
         if (n > caps.points) caps.points = grow_to((unsigned int) n, 4096);
@@ -391,6 +392,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
                 graph_caps = caps;
                 graph_frontend_only = (int) frontend_only;
                 graph_launches = launches;
+                ++call_captures;
             }
             LA3DM_CUDA(cudaGraphLaunch(graph_exec, stream));
             launches = graph_launches;
@@ -406,6 +408,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (!ovf) break;
         // a workspace was too small: nothing was written to the map; grow from the sizes the device reports and replay
         ++replays;
+        ++call_replays;
         if (ovf & OVF_EXTENT) throw StatusError{LA3DM_ERR_EXTENT, "scan bounding box spans too many blocks"};
         if (ovf & OVF_VGCELLS) {   // only the bit count matters (radix-sort passes): next power of two
             unsigned int v = 1u << 20;
@@ -436,6 +439,8 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     stats.n_blocks_total = n_blocks;
     stats.new_blocks = h_cnt->n_new_blocks;
     stats.kernel_launches = launches;
+    stats.replays = call_replays;
+    stats.graph_captures = call_captures;
     stats.grid_irregular = (int32_t) h_cnt->grid_irregular;
     stats.h2d_bytes = h2d_bytes + (long long) sizeof(ScanArgs);   // h2d_bytes: the cloud, set by the host entry point
     stats.d2h_bytes = d2h_bytes;
