@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Leaf) == 56
     assert C.sizeof(_lib.Params) == 16 * 4
     assert _lib.Leaf.block_key.offset == 0 and _lib.Leaf.x.offset == 16 and _lib.Leaf.state.offset == 48
-    assert C.sizeof(_lib.ScanStats) == 10 * 8 + 4 * 4 + 2 * 8
+    assert C.sizeof(_lib.ScanStats) == 10 * 8 + 4 * 4 + 2 * 8 + 2 * 4
 
 
 def test_abi_version_and_status_strings():
