@@ -22,6 +22,8 @@
 // k_predict_bgk_deep (block_depth 4): plain formulation, 16 slots per lane, works on the record in global memory.
 //
 // Bound: issue slots / FP32 pipe (~24 flop per pair vs 17 B per voxel visit).
+#include <stdlib.h>
+
 #include "block_common.cuh"
 
 namespace la3dm_b200 {
@@ -351,6 +353,391 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__
     }
 }
 
+// ---- k_predict_bgk_oct: block_depth == 3.  EIGHT lanes per test block, FOUR test blocks per warp. -----------------------
+// Lane o of a block owns child o of every depth-1 octant: slot s = finest voxel 9 + 8s + o (so the pairs of a training
+// point, which cluster in one or two octants, spread evenly over the 8 lanes).  If octant o is pruned, lane o's slot o
+// holds the depth-1 leaf 1 + o instead (no lane has a voxel there); if the whole block is pruned, lane 0's slot 0 holds
+// the root.
+//   * the record never goes through a staging copy: a lane loads the (m_A, m_B) pairs and state bytes of its own nodes
+//     (8 lanes x 8 bytes = one 64-byte line per load), keeps the floats in a per-lane column of shared memory (indexed
+//     by slot at run time) and writes back only what changed;
+//   * the per-axis centre coordinates of a lane's voxels are separable (init_key_loc_map, bgkblock.cpp:7-32: bits
+//     4 / 2 / 1 of a child index pick x / y / z at every level), so one point costs 6 differences and 6 squares for 8
+//     voxels;
+//   * a tile = up to 8 points per block; points that cannot reach the hull of the block's leaf centres are dropped when
+//     the tile is loaded (order preserved); the support test leaves one bit per (point, slot) in a 64-bit register;
+//   * the pairs inside the support are numbered by one warp scan, their squared distances go to a shared queue, the
+//     kernel function (sqrt, sin, cos) is evaluated DENSELY over the queue by all 32 lanes, and every lane adds its own
+//     pairs to (ybar, kbar) in training-array order -- the order of fp32 additions of the CPU path; a pair from a new
+//     neighbour closes the previous neighbour's sums (Occupancy::update if kbar > 0, ExtendedBlock order);
+//     classification once per touched leaf; OcTree::prune by votes of the block's 8 lanes.
+constexpr int kOctQCap = 256;         // queue entries per warp (one point against 4 x 64 voxels always fits)
+constexpr int kOctStride = 9;         // float4 per block in the point tile: 8 + 1 so the 4 broadcasts hit distinct banks
+
+struct OctSmem {
+    float a[8][32], b[8][32];         // [slot][lane]: m_A, m_B
+    float yb[8][32], kb[8][32];       // [slot][lane]: sums over the current neighbour
+    float4 pts[4 * kOctStride];       // surviving points of the current tile, per block
+    float qd[kOctQCap];               // squared distance in, kernel value out
+    unsigned char nb[32];             // neighbour (0..6) of each tile point
+};
+
+template <int kMinCtas>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtas)
+k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
+                  const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
+                  const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt) {
+    __shared__ OctSmem sm[kWarpsPerCta];
+    __shared__ DevParams Ps;
+    if (threadIdx.x < sizeof(DevParams) / 4)
+        reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    __syncthreads();
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, o = lane & 7, gbase = lane & 24;
+    const unsigned int full = 0xffffffffu;
+    OctSmem &S = sm[warp];
+    float4 *tile = S.pts + g * kOctStride;
+    unsigned char *tnb = S.nb + g * 8;
+    const unsigned int T = cnt->n_test_blocks;
+    const unsigned int units_total = gridDim.x * kWarpsPerCta * 4;
+    const int nodes = P.nodes, st_off = P.st_off;
+    const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
+    const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
+    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
+    // every leaf centre lies within (block_size - resolution) / 2 of the block centre (conservative, in units of ell)
+    const float reach = 0.5f * (bs - P.resolution) * 1.001f / ell;
+    const float cull2 = 1.0f + 1e-4f;
+    const float def_a = P.def_a, def_b = P.def_b;
+    // centre offsets (block-relative) of child o of octants 0 / 4 / 2 / 1, of node 1 + o and of the root
+    const float3 lf0 = lut[9 + o], lfx = lut[9 + 32 + o], lfy = lut[9 + 16 + o], lfz = lut[9 + 8 + o];
+    const float3 l1 = lut[1 + o], l0 = lut[0];
+
+    unsigned long long visits = 0, updates = 0, pairs = 0;
+
+    // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over (warp, group)
+    for (unsigned int u0 = (blockIdx.x * kWarpsPerCta + warp) * 4;; u0 += units_total) {
+        if (u0 * shard_world + shard_rank >= T) break;                    // warp-uniform: group 0 has the smallest t
+        const unsigned int t = (u0 + (unsigned int) g) * shard_world + shard_rank;
+        const bool have = t < T;
+        // ---- plan: lanes o = 0..6 of a group hold start / count of neighbour o
+        unsigned int my_start = 0, my_count = 0, slot = 0, is_new = 0;
+        if (have) {
+            const NeighbourPlan *pl = plan + t;
+            if (o < 7) { my_start = pl->start[o]; my_count = pl->count[o]; }
+            slot = pl->slot;
+            is_new = pl->is_new;
+        }
+        unsigned int pre = my_count;                                      // inclusive prefix inside the group
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const unsigned int up = __shfl_up_sync(full, pre, d, 8);
+            if (o >= d) pre += up;
+        }
+        const unsigned int tot = __shfl_sync(full, pre, 7, 8);
+        pre -= my_count;                                                  // exclusive
+        unsigned int max_tot = tot;
+        max_tot = max(max_tot, __shfl_xor_sync(full, max_tot, 8));
+        max_tot = max(max_tot, __shfl_xor_sync(full, max_tot, 16));
+
+        unsigned char *rec = pool + (size_t) slot * (size_t) P.rec_bytes;
+        float2 *gab = reinterpret_cast<float2 *>(rec);
+        unsigned char *gst = rec + st_off;
+
+        // ---- this lane's part of the record: floats -> its shared-memory column, states -> a packed register pair
+        unsigned int stlo = 0x02020202u, sthi = 0x02020202u;             // LA3DM_UNKNOWN x 8 (slot s: byte s)
+        float2 ab1 = make_float2(def_a, def_b), ab0 = make_float2(def_a, def_b);
+        unsigned int st1 = LA3DM_UNKNOWN, st0 = LA3DM_UNKNOWN, st_oct = LA3DM_UNKNOWN;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        __syncwarp();
+        if (have && !is_new) {
+            unsigned int sb[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const float2 v = gab[9 + 8 * s + o];
+                S.a[s][lane] = v.x; S.b[s][lane] = v.y;
+                sb[s] = gst[9 + 8 * s + o];
+            }
+            stlo = sb[0] | (sb[1] << 8) | (sb[2] << 16) | (sb[3] << 24);
+            sthi = sb[4] | (sb[5] << 8) | (sb[6] << 16) | (sb[7] << 24);
+            ab1 = gab[1 + o]; st1 = gst[1 + o];
+            ab0 = gab[0]; st0 = gst[0];
+            st_oct = gst[9 + 8 * o];                                     // child 0 of octant o: PRUNED <=> octant o is pruned
+        } else {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) { S.a[s][lane] = def_a; S.b[s][lane] = def_b; }
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) { S.yb[s][lane] = 0.f; S.kb[s][lane] = 0.f; }
+        if (have) {
+            // block centre from its key (hash_key_to_block, bgkblock.cpp:79-83)
+            const long long key = keys[slot];
+            cx = axis_center(key >> 40, bs); cy = axis_center((key >> 20) & 0xFFFFF, bs); cz = axis_center(key & 0xFFFFF, bs);
+        }
+        // ---- leaves owned by this lane (is_leaf, bgkoctree.cpp:72-82).  A finest voxel is a leaf unless PRUNED; node
+        // 1 + o is a leaf if it is not PRUNED and its children are; the root is a leaf if its children are PRUNED.
+        const unsigned int st1_first = __shfl_sync(full, st1, 0, 8);
+        const bool root_leaf = have && (st1_first & 7u) == kStPRUNED;
+        const bool d1_leaf = have && !root_leaf && (st_oct & 7u) == kStPRUNED;
+        const bool coarse = d1_leaf || (root_leaf && o == 0);            // lane's slot `cs` holds a coarse leaf
+        const int cs = root_leaf ? 0 : o;
+        // existing regular slots: byte s of the state words != PRUNED
+        unsigned int vm = 0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const unsigned int sv = ((s < 4 ? stlo : sthi) >> (8 * (s & 3))) & 7u;
+            if (have && sv != (unsigned int) kStPRUNED) vm |= 1u << s;
+        }
+        float ccx_ = 0.f, ccy_ = 0.f, ccz_ = 0.f;                        // centre of the coarse leaf, / ell
+        if (coarse) {
+            const float2 v = root_leaf ? ab0 : ab1;
+            const unsigned int sv = root_leaf ? st0 : st1;
+            S.a[cs][lane] = v.x; S.b[cs][lane] = v.y;
+            if (cs < 4) stlo = (stlo & ~(0xFFu << (8 * cs))) | (sv << (8 * cs));
+            else sthi = (sthi & ~(0xFFu << (8 * (cs - 4)))) | (sv << (8 * (cs - 4)));
+            const float3 off = root_leaf ? l0 : l1;
+            ccx_ = (off.x + cx) / ell; ccy_ = (off.y + cy) / ell; ccz_ = (off.z + cz) / ell;
+            vm |= 1u << cs;
+        }
+        // Block::get_loc (bgkblock.h:64-66): LUT offset + centre, then covSparse's  xs / ell  (bgkinference.h:114)
+        const float x0 = (lf0.x + cx) / ell, y0 = (lf0.y + cy) / ell, z0 = (lf0.z + cz) / ell;
+        const float x1 = (lfx.x + cx) / ell, y1 = (lfy.y + cy) / ell, z1 = (lfz.z + cz) / ell;
+        const float ccx = cx / ell, ccy = cy / ell, ccz = cz / ell;
+        const unsigned int cbit = coarse ? (1u << cs) : 0u;
+        const int nleaf = __popc(vm);
+        visits += (unsigned long long) nleaf;
+        pairs += (unsigned long long) nleaf * tot;
+
+        unsigned int lastnb = 0xFFFFFFFFu;         // per slot (4 bits): neighbour whose sums are being accumulated
+        unsigned int touched = 0;                  // per slot: Occupancy::update ran
+
+        // ---- stream the points of the 7 neighbours (ranges concatenated in ExtendedBlock order), 8 per block at a time
+        for (unsigned int base = 0; base < max_tot; base += 8) {
+            const unsigned int gi = base + (unsigned int) o;
+            const bool valid = gi < tot;
+            unsigned int nbi = 0;
+#pragma unroll
+            for (int k = 1; k < 7; ++k) nbi += (gi >= __shfl_sync(full, pre, k, 8)) ? 1u : 0u;
+            const unsigned int nb_start = __shfl_sync(full, my_start, (int) nbi, 8);
+            const unsigned int nb_pre = __shfl_sync(full, pre, (int) nbi, 8);
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool keep = false;
+            if (valid) {
+                z = pts[nb_start + (gi - nb_pre)];
+                const float rx = fmaxf(fabsf(z.x - ccx) - reach, 0.f), ry = fmaxf(fabsf(z.y - ccy) - reach, 0.f),
+                            rz = fmaxf(fabsf(z.z - ccz) - reach, 0.f);
+                keep = (rx * rx + (ry * ry + rz * rz)) < cull2;
+            }
+            const unsigned int kept = __ballot_sync(full, keep);
+            const unsigned int gk = (kept >> gbase) & 0xFFu;
+            const int nsurv = __popc(gk);
+            const int max_surv = max(max(__popc(kept & 0xFFu), __popc(kept & 0xFF00u)),
+                                     max(__popc(kept & 0xFF0000u), __popc(kept & 0xFF000000u)));
+            if (max_surv == 0) continue;
+            __syncwarp();
+            if (keep) {
+                const int pos = __popc(gk & ((1u << o) - 1u));
+                tile[pos] = z;
+                tnb[pos] = (unsigned char) nbi;
+            }
+            __syncwarp();
+
+            // ---- support test: bit 8q + s of m  <=>  point q is within ell of this lane's slot s
+            unsigned long long m = 0;
+            for (int q = 0; q < max_surv; ++q) {
+                const float4 zq = tile[q];
+                const float dx0 = zq.x - x0, dx1 = zq.x - x1, dy0 = zq.y - y0, dy1 = zq.y - y1, dz0 = zq.z - z0,
+                            dz1 = zq.z - z1;
+                const float xx0 = dx0 * dx0, xx1 = dx1 * dx1;
+                const float yy0 = dy0 * dy0, yy1 = dy1 * dy1, zz0 = dz0 * dz0, zz1 = dz1 * dz1;
+                const float s00 = yy0 + zz0, s01 = yy0 + zz1, s10 = yy1 + zz0, s11 = yy1 + zz1;   // [y bit][z bit]
+                // d2 = dx*dx + (dy*dy + dz*dz): Eigen rowwise().norm() of a 3-vector, squared; k <= 0 for d >= 1
+                unsigned int in = ((xx0 + s00) < 1.0f ? 1u : 0u) | ((xx0 + s01) < 1.0f ? 2u : 0u) |
+                                  ((xx0 + s10) < 1.0f ? 4u : 0u) | ((xx0 + s11) < 1.0f ? 8u : 0u) |
+                                  ((xx1 + s00) < 1.0f ? 16u : 0u) | ((xx1 + s01) < 1.0f ? 32u : 0u) |
+                                  ((xx1 + s10) < 1.0f ? 64u : 0u) | ((xx1 + s11) < 1.0f ? 128u : 0u);
+                if (coarse) {
+                    const float dx = zq.x - ccx_, dy = zq.y - ccy_, dz = zq.z - ccz_;
+                    in = (in & ~cbit) | ((dx * dx + (dy * dy + dz * dz)) < 1.0f ? cbit : 0u);
+                }
+                if (q < nsurv) m |= (unsigned long long) (in & vm) << (8 * q);
+            }
+            const unsigned int cnt_l = (unsigned int) __popcll(m);
+            unsigned int inc = cnt_l;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int up = __shfl_up_sync(full, inc, d);
+                if (lane >= d) inc += up;
+            }
+            const unsigned int total = __shfl_sync(full, inc, 31);
+            if (total == 0) continue;
+            // the queue holds kOctQCap pairs: a tile with more is taken one point (of each block) at a time
+            const bool split = total > (unsigned int) kOctQCap;
+            const int n_parts = split ? max_surv : 1;
+            for (int part = 0; part < n_parts; ++part) {
+                unsigned long long pm = m;
+                unsigned int off = inc - cnt_l, ptotal = total;
+                if (split) {
+                    pm &= 0xFFull << (8 * part);
+                    const unsigned int c2 = (unsigned int) __popcll(pm);
+                    unsigned int i2 = c2;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned int up = __shfl_up_sync(full, i2, d);
+                        if (lane >= d) i2 += up;
+                    }
+                    ptotal = __shfl_sync(full, i2, 31);
+                    off = i2 - c2;
+                    if (ptotal == 0) continue;
+                }
+                // squared distances of this lane's pairs -> queue (points in order)
+                {
+                    unsigned int e = off;
+                    unsigned long long w = pm;
+                    while (w) {
+                        const int bit = __ffsll((long long) w) - 1;
+                        w &= w - 1;
+                        const int q = bit >> 3, s = bit & 7;
+                        float xc = (s & 4) ? x1 : x0, yc = (s & 2) ? y1 : y0, zc = (s & 1) ? z1 : z0;
+                        if ((cbit >> s) & 1u) { xc = ccx_; yc = ccy_; zc = ccz_; }
+                        const float4 zq = tile[q];
+                        const float dx = zq.x - xc, dy = zq.y - yc, dz = zq.z - zc;
+                        S.qd[e++] = dx * dx + (dy * dy + dz * dz);
+                    }
+                }
+                __syncwarp();
+                for (unsigned int i = lane; i < ptotal; i += 32) S.qd[i] = sparse_kernel(sqrtf(S.qd[i]), sf2);
+                __syncwarp();
+                // every lane adds its own pairs; the first pair of a new neighbour closes the previous neighbour:
+                // Occupancy::update's accumulation (bgkoctree_node.cpp:31-35) if kbar > 0 (bgkoctomap.cpp:332)
+                {
+                    unsigned int e = off;
+                    unsigned long long w = pm;
+                    while (w) {
+                        const int bit = __ffsll((long long) w) - 1;
+                        w &= w - 1;
+                        const int q = bit >> 3, s = bit & 7;
+                        const unsigned int nbq = tnb[q];
+                        const float wq = tile[q].w;
+                        const float k = S.qd[e++];
+                        float ybv = S.yb[s][lane], kbv = S.kb[s][lane];
+                        if (nbq != ((lastnb >> (4 * s)) & 0xFu)) {
+                            if (kbv > 0.0f) {
+                                S.a[s][lane] += ybv;
+                                S.b[s][lane] += kbv - ybv;
+                                touched |= 1u << s;
+                            }
+                            ybv = 0.f; kbv = 0.f;
+                            lastnb = (lastnb & ~(0xFu << (4 * s))) | (nbq << (4 * s));
+                        }
+                        S.yb[s][lane] = ybv + k * wq;
+                        S.kb[s][lane] = kbv + k;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- the last neighbour, then the rest of Occupancy::update (bgkoctree_node.cpp:36-43) once per touched leaf
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const float kbv = S.kb[s][lane];
+            float av = S.a[s][lane], bv = S.b[s][lane];
+            if (kbv > 0.0f) {
+                const float ybv = S.yb[s][lane];
+                av += ybv; bv += kbv - ybv;
+                S.a[s][lane] = av; S.b[s][lane] = bv;
+                touched |= 1u << s;
+            }
+            if ((touched >> s) & 1u) {
+                const unsigned int ns = (unsigned int) bgk_classify(av, bv, U) | 0x80u;
+                if (s < 4) stlo = (stlo & ~(0xFFu << (8 * s))) | (ns << (8 * s));
+                else sthi = (sthi & ~(0xFFu << (8 * (s - 4)))) | (ns << (8 * (s - 4)));
+                ++updates;
+            }
+        }
+        const unsigned int dirty_lanes = __ballot_sync(full, touched != 0u);
+        const bool dirty = have && (((dirty_lanes >> gbase) & 0xFFu) != 0u || is_new != 0u);
+        __syncwarp();                               // lane 0's column is read by the other lanes below
+
+        // ---- OcTree::prune (bgkoctree.cpp:101-148).  Layer 2 -> 1: octant s collapses if its 8 voxels (slot s of the
+        // block's 8 lanes) share FREE or OCCUPIED; node 1 + s takes child 0's floats and state (`classified` is not
+        // copied, bgkoctree_node.h:40-45), the voxels become PRUNED
+        unsigned int pr2 = 0, pr2_occ = 0;          // octants pruned now / as OCCUPIED (same in the block's 8 lanes)
+        const unsigned int regular = vm & ~cbit;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const unsigned int sv = ((s < 4 ? stlo : sthi) >> (8 * (s & 3))) & 7u;
+            const bool reg = (regular >> s) & 1u;
+            const unsigned int fv = (__ballot_sync(full, reg && sv == LA3DM_FREE) >> gbase) & 0xFFu;
+            const unsigned int ov = (__ballot_sync(full, reg && sv == LA3DM_OCCUPIED) >> gbase) & 0xFFu;
+            if (fv == 0xFFu || ov == 0xFFu) {
+                pr2 |= 1u << s;
+                if (ov == 0xFFu) pr2_occ |= 1u << s;
+                if (s < 4) stlo = (stlo & ~(7u << (8 * s))) | ((unsigned int) kStPRUNED << (8 * s));
+                else sthi = (sthi & ~(7u << (8 * (s - 4)))) | ((unsigned int) kStPRUNED << (8 * (s - 4)));
+            }
+        }
+        // current depth-1 node 1 + o of this lane
+        float2 c1ab = ab1;
+        unsigned int c1st = st1;
+        const unsigned int my_byte = ((o < 4 ? stlo : sthi) >> (8 * (o & 3))) & 0xFFu;    // state byte of slot o
+        if (d1_leaf) { c1ab = make_float2(S.a[o][lane], S.b[o][lane]); c1st = my_byte; }
+        const bool pr2_mine = (pr2 >> o) & 1u;
+        if (pr2_mine) {          // child 0 of octant o is slot o of the block's first lane
+            c1ab = make_float2(S.a[o][gbase], S.b[o][gbase]);
+            c1st = (st1 & 0x80u) | (((pr2_occ >> o) & 1u) ? (unsigned int) LA3DM_OCCUPIED : (unsigned int) LA3DM_FREE);
+        }
+        // layer 1 -> 0: the 8 depth-1 nodes vote
+        const unsigned int f1 = (__ballot_sync(full, (c1st & 7u) == LA3DM_FREE) >> gbase) & 0xFFu;
+        const unsigned int o1 = (__ballot_sync(full, (c1st & 7u) == LA3DM_OCCUPIED) >> gbase) & 0xFFu;
+        const bool pr1 = have && (f1 == 0xFFu || o1 == 0xFFu);
+        const float c1a_first = __shfl_sync(full, c1ab.x, 0, 8), c1b_first = __shfl_sync(full, c1ab.y, 0, 8);
+        float2 c0ab = ab0;
+        unsigned int c0st = st0;
+        if (root_leaf && o == 0) { c0ab = make_float2(S.a[0][lane], S.b[0][lane]); c0st = stlo & 0xFFu; }
+        if (pr1) {
+            c0ab = make_float2(c1a_first, c1b_first);
+            c0st = (st0 & 0x80u) | (c1st & 7u);
+            c1st = (c1st & 0x80u) | (unsigned int) kStPRUNED;
+        }
+        // ---- write back what changed (a fresh block: everything)
+        if (dirty) {
+            const bool all = is_new != 0u;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (!((regular >> s) & 1u)) continue;
+                const bool tch = (touched >> s) & 1u;
+                if (all || tch) gab[9 + 8 * s + o] = make_float2(S.a[s][lane], S.b[s][lane]);
+                if (all || tch || ((pr2 >> s) & 1u))
+                    gst[9 + 8 * s + o] = (unsigned char) (((s < 4 ? stlo : sthi) >> (8 * (s & 3))) & 0xFFu);
+            }
+            const bool d1_touched = d1_leaf && ((touched >> o) & 1u);
+            if (all || pr2_mine || d1_touched) gab[1 + o] = c1ab;
+            if (all || pr2_mine || d1_touched || pr1) gst[1 + o] = (unsigned char) c1st;
+            if (o == 0) {
+                if (all || pr1 || (root_leaf && (touched & 1u))) { gab[0] = c0ab; gst[0] = (unsigned char) c0st; }
+                // leaf count behind the states (read by k_predict_bgk's early-out)
+                gst[nodes] = (unsigned char) ((pr1 || root_leaf) ? 1u : 8u + 7u * (unsigned int) __popc(regular & ~pr2));
+            } else if (all) {
+                for (int n = st_off + nodes + 2 * o - 1; n < P.rec_bytes && n <= st_off + nodes + 2 * o; ++n) rec[n] = 0;
+            }
+        }
+    }
+
+    // stats: one atomic per warp
+    for (int d = 16; d > 0; d >>= 1) {
+        visits += __shfl_xor_sync(full, visits, d);
+        updates += __shfl_xor_sync(full, updates, d);
+        pairs += __shfl_xor_sync(full, pairs, d);
+    }
+    if (lane == 0 && visits) {
+        atomicAdd(&cnt->visits, visits);
+        atomicAdd(&cnt->updates, updates);
+        atomicAdd(&cnt->pairs, pairs);
+    }
+}
+
 // ---- block_depth 4: 512 finest voxels per block, 16 slots per lane, record updated in global memory ----------------
 constexpr int kDeepSlots = 16;
 
@@ -504,8 +891,17 @@ __global__ void k_scan_end(ScanCounters *c, const ScanArgs *__restrict__ A) {
 void Map::enqueue_predict() {
     if (hp.method != LA3DM_BGK) throw StatusError{LA3DM_ERR_UNSUPPORTED, "predict: method not implemented yet"};
     const int ctas = num_sms * 4;
+    static const bool force_v1 = getenv("LA3DM_PREDICT_V1") != nullptr;     // debugging: the one-warp-per-block kernel
     record_event(ev_p0);
-    if (hp.depth <= 3)
+    if (hp.depth == 3 && !force_v1) {
+        static const int oct_ctas = getenv("LA3DM_OCT_CTAS") ? atoi(getenv("LA3DM_OCT_CTAS")) : 3;
+        const int n = oct_ctas == 2 ? 2 : (oct_ctas == 4 ? 4 : 3);
+        auto kern = n == 2 ? k_predict_bgk_oct<2> : (n == 4 ? k_predict_bgk_oct<4> : k_predict_bgk_oct<3>);
+        kern<<<num_sms * n, kWarpsPerCta * 32, 0, stream>>>(
+            plan.as<NeighbourPlan>(), pts_sorted.as<float4>(), keys.as<long long>(), pool.as<unsigned char>(), d_lut,
+            d_params, d_args, d_cnt);
+    }
+    else if (hp.depth <= 3)
         k_predict_bgk<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
                                                               keys.as<long long>(), pool.as<unsigned char>(), d_lut,
                                                               d_params, d_args, d_cnt);
