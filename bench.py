@@ -355,6 +355,9 @@ def run_ours(a):
         fp32 = ctypes.c_float(0)
         la3dm_b200.load().la3dm_bench_fp32_peak(local, ctypes.byref(fp32))
         k_ms = float(np.mean([pred_ms[s] for s in timed]))
+        if os.environ.get("LA3DM_BENCH_VERBOSE"):
+            sys.stderr.write("per-scan ms (device-resident pass): step %s\n" % " ".join("%.4f" % ms_d[s] for s in timed))
+            sys.stderr.write("per-scan ms: predict %s\n" % " ".join("%.4f" % pred_ms[s] for s in timed))
         k_bytes = float(np.mean([BYTES_PER_VISIT * vis[s] / world + BYTES_PER_MEMBER * st_d[s]["n_train"] +
                                  BYTES_PER_TEST_BLOCK * st_d[s]["n_test_blocks"] / world for s in timed]))
         k_flop = float(np.mean([FLOP_PER_PAIR * pairs[s] / world for s in timed]))

@@ -226,7 +226,8 @@ __global__ void k_db_place(const unsigned int *__restrict__ keys, const unsigned
         ++pos;
         const int z = (int) (id % (unsigned int) nz), y = (int) ((id / (unsigned int) nz) % (unsigned int) ny),
                   x = (int) (id / ((unsigned int) nz * (unsigned int) ny));
-        const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
+        unsigned int tot = 0;
+    const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
             const int xx = x + dx[q], yy = y + dy[q], zz = z + dz[q];
@@ -322,7 +323,7 @@ __device__ inline void hash_insert(long long *hkeys, int *hvals, size_t mask, lo
 __global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs *__restrict__ A,
                        const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
                        const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask,
-                       long long *keys, NeighbourPlan *plan, unsigned int *plan_db) {
+                       long long *keys, NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list) {
     const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (c->overflow || t >= c->n_test_blocks) return;
     const unsigned int id = test_id[t];
@@ -339,6 +340,7 @@ __global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c
         hash_insert(hkeys, hvals, mask, key, slot);
     }
     pl.slot = (unsigned int) slot;
+    unsigned int tot = 0;
     const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -353,7 +355,9 @@ __global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c
         } else if (plan_db) plan_db[(size_t) t * 8 + k] = 0;
         pl.start[k] = start;
         pl.count[k] = count;
+        tot += count;
     }
+    if (heavy_list && tot > kHeavyTot) heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
     uint4 *dst = reinterpret_cast<uint4 *>(plan + t);
     const uint4 *src = reinterpret_cast<const uint4 *>(&pl);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -460,7 +464,8 @@ void Map::enqueue_binning() {
         test_id.as<unsigned int>(), d_cnt, d_args, d_grid, cell_db.as<unsigned int>(),
         hp.method == LA3DM_BGKL ? seg_start.as<unsigned int>() : db_start.as<unsigned int>(),
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
-        hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr);
+        hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr,
+        hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr);
     launches += 3;
 }
 

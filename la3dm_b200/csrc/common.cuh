@@ -76,6 +76,7 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxDepth = 6;        // node index is unsigned short upstream (bgkoctree.cpp:9-16): fine up to depth 6
 constexpr int kMaxAxis = 8192;      // per-axis capacity of the float-stepped block grid (blocks per axis per scan)
+constexpr unsigned int kHeavyTot = 64;   // test blocks above this many neighbourhood points are predicted first
 constexpr int kStPRUNED = 3;        // BGK/BGKL/GP numbering; BGKLV uses 4 (see include/la3dm_b200.h)
 
 struct DevParams {
@@ -175,7 +176,9 @@ struct ScanCounters {
     unsigned int vg_cells_needed;
     unsigned int gp_n_max;       // GP: largest data block of the scan
     unsigned int lv_active;      // BGKLV: active voxels of the scan
-    unsigned int pad_;
+    unsigned int work_next;      // dynamic work distribution of the predict kernel (units handed out so far)
+    unsigned int n_heavy;        // test blocks with more than kHeavyTot training points in their ExtendedBlock
+    unsigned int pad2_;
     unsigned long long gp_store_needed;
 };
 

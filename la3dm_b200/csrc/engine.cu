@@ -309,6 +309,7 @@ void Map::ensure_workspace() {
     moved |= test_bits.reserve(((size_t) caps.cells / 32 + 2) * 4, stream);
     moved |= test_id.reserve((size_t) caps.tests * 4, stream);
     moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
+    moved |= heavy_list.reserve((size_t) caps.tests * 4, stream);
     if (hp.method == LA3DM_BGKLV) {
         moved |= lv_range.reserve((size_t) caps.points * 8, stream);
         moved |= lv_info.reserve((size_t) caps.points * lv_ray_info_bytes(), stream);

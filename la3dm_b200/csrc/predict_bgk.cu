@@ -371,24 +371,29 @@ k_predict_bgk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__
 //     pairs to (ybar, kbar) in training-array order -- the order of fp32 additions of the CPU path; a pair from a new
 //     neighbour closes the previous neighbour's sums (Occupancy::update if kbar > 0, ExtendedBlock order);
 //     classification once per touched leaf; OcTree::prune by votes of the block's 8 lanes.
-constexpr int kOctQCap = 256;         // queue entries per warp (one point against 4 x 64 voxels always fits)
 constexpr int kOctStride = 9;         // float4 per block in the point tile: 8 + 1 so the 4 broadcasts hit distinct banks
+constexpr int kStripStride = 65;      // floats per lane in the pair strips: 8 points x 8 slots (+1: bank spread)
 
 struct OctSmem {
     float a[8][32], b[8][32];         // [slot][lane]: m_A, m_B
     float yb[8][32], kb[8][32];       // [slot][lane]: sums over the current neighbour
+    float strip[32 * kStripStride];   // per lane: squared distances of its in-support pairs in, kernel values out
     float4 pts[4 * kOctStride];       // surviving points of the current tile, per block
-    float qd[kOctQCap];               // squared distance in, kernel value out
+    unsigned int inc[32];             // inclusive scan of the lanes' pair counts
     unsigned char nb[32];             // neighbour (0..6) of each tile point
+    unsigned char lnb[8][32];         // [slot][lane]: neighbour whose sums are being accumulated (0xFF: none yet)
 };
+constexpr size_t kOctSmemBytes = sizeof(OctSmem) * kWarpsPerCta + sizeof(DevParams);
 
 template <int kMinCtas>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kMinCtas)
 k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
                   const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
-                  const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt) {
-    __shared__ OctSmem sm[kWarpsPerCta];
-    __shared__ DevParams Ps;
+                  const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt,
+                  const unsigned int *__restrict__ heavy_list) {
+    extern __shared__ __align__(16) unsigned char oct_smem_raw[];
+    OctSmem *sm = reinterpret_cast<OctSmem *>(oct_smem_raw);
+    DevParams &Ps = *reinterpret_cast<DevParams *>(oct_smem_raw + sizeof(OctSmem) * kWarpsPerCta);
     if (threadIdx.x < sizeof(DevParams) / 4)
         reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
     __syncthreads();
@@ -401,7 +406,6 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
     float4 *tile = S.pts + g * kOctStride;
     unsigned char *tnb = S.nb + g * 8;
     const unsigned int T = cnt->n_test_blocks;
-    const unsigned int units_total = gridDim.x * kWarpsPerCta * 4;
     const int nodes = P.nodes, st_off = P.st_off;
     const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
     const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
@@ -416,11 +420,29 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
 
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
-    // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over (warp, group)
-    for (unsigned int u0 = (blockIdx.x * kWarpsPerCta + warp) * 4;; u0 += units_total) {
-        if (u0 * shard_world + shard_rank >= T) break;                    // warp-uniform: group 0 has the smallest t
-        const unsigned int t = (u0 + (unsigned int) g) * shard_world + shard_rank;
-        const bool have = t < T;
+    // Work units of 4 test blocks are handed out through one atomic counter.  The heavy blocks (more than kHeavyTot
+    // neighbourhood points, listed by k_plan) go first, four of similar weight to a warp; then all test blocks in
+    // cell order, the heavy ones skipped.  Test block t belongs to rank t % world.
+    const unsigned int n_heavy = heavy_list ? cnt->n_heavy : 0u;
+    const unsigned int heavy_units = (n_heavy + 3u) >> 2;
+    const unsigned int T_mine = T > shard_rank ? (T - shard_rank + shard_world - 1u) / shard_world : 0u;
+    const unsigned int units = heavy_units + ((T_mine + 3u) >> 2);
+    unsigned int w_next = 0;
+    if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);
+    for (;;) {
+        const unsigned int w = __shfl_sync(full, w_next, 0);
+        if (w >= units) break;
+        if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);          // in flight while this unit is processed
+        unsigned int t = 0;
+        bool have;
+        if (w < heavy_units) {
+            const unsigned int idx = 4u * w + (unsigned int) g;
+            have = idx < n_heavy;
+            if (have) { t = heavy_list[idx]; have = t % shard_world == shard_rank; }
+        } else {
+            t = (4u * (w - heavy_units) + (unsigned int) g) * shard_world + shard_rank;
+            have = t < T;
+        }
         // ---- plan: lanes o = 0..6 of a group hold start / count of neighbour o
         unsigned int my_start = 0, my_count = 0, slot = 0, is_new = 0;
         if (have) {
@@ -428,6 +450,11 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
             if (o < 7) { my_start = pl->start[o]; my_count = pl->count[o]; }
             slot = pl->slot;
             is_new = pl->is_new;
+        }
+        if (heavy_list && w >= heavy_units) {          // a heavy block met in cell order was done in the first phase
+            unsigned int sum = my_count;
+            sum += __shfl_xor_sync(full, sum, 1); sum += __shfl_xor_sync(full, sum, 2); sum += __shfl_xor_sync(full, sum, 4);
+            if (sum > kHeavyTot) { have = false; my_count = 0; is_new = 0; }
         }
         unsigned int pre = my_count;                                      // inclusive prefix inside the group
 #pragma unroll
@@ -469,7 +496,7 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
             for (int s = 0; s < 8; ++s) { S.a[s][lane] = def_a; S.b[s][lane] = def_b; }
         }
 #pragma unroll
-        for (int s = 0; s < 8; ++s) { S.yb[s][lane] = 0.f; S.kb[s][lane] = 0.f; }
+        for (int s = 0; s < 8; ++s) { S.yb[s][lane] = 0.f; S.kb[s][lane] = 0.f; S.lnb[s][lane] = 0xFFu; }
         if (have) {
             // block centre from its key (hash_key_to_block, bgkblock.cpp:79-83)
             const long long key = keys[slot];
@@ -505,11 +532,13 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
         const float x1 = (lfx.x + cx) / ell, y1 = (lfy.y + cy) / ell, z1 = (lfz.z + cz) / ell;
         const float ccx = cx / ell, ccy = cy / ell, ccz = cz / ell;
         const unsigned int cbit = coarse ? (1u << cs) : 0u;
+        const unsigned int regular = vm & ~cbit;
+        const bool any_coarse = __ballot_sync(full, coarse) != 0u;
+        float *strip = S.strip + lane * kStripStride;
         const int nleaf = __popc(vm);
         visits += (unsigned long long) nleaf;
         pairs += (unsigned long long) nleaf * tot;
 
-        unsigned int lastnb = 0xFFFFFFFFu;         // per slot (4 bits): neighbour whose sums are being accumulated
         unsigned int touched = 0;                  // per slot: Occupancy::update ran
 
         // ---- stream the points of the 7 neighbours (ranges concatenated in ExtendedBlock order), 8 per block at a time
@@ -543,8 +572,10 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
             }
             __syncwarp();
 
-            // ---- support test: bit 8q + s of m  <=>  point q is within ell of this lane's slot s
-            unsigned long long m = 0;
+            // ---- support test: bit 8 (q & 3) + s of mlo (q < 4) / mhi (q >= 4)  <=>  point q is within ell of this lane's
+            // regular slot s; the squared distance of every such pair goes to the lane's strip (point-major order)
+            unsigned int mlo = 0, mhi = 0, mco = 0;
+            unsigned int n = 0;
             for (int q = 0; q < max_surv; ++q) {
                 const float4 zq = tile[q];
                 const float dx0 = zq.x - x0, dx1 = zq.x - x1, dy0 = zq.y - y0, dy1 = zq.y - y1, dz0 = zq.z - z0,
@@ -553,18 +584,32 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
                 const float yy0 = dy0 * dy0, yy1 = dy1 * dy1, zz0 = dz0 * dz0, zz1 = dz1 * dz1;
                 const float s00 = yy0 + zz0, s01 = yy0 + zz1, s10 = yy1 + zz0, s11 = yy1 + zz1;   // [y bit][z bit]
                 // d2 = dx*dx + (dy*dy + dz*dz): Eigen rowwise().norm() of a 3-vector, squared; k <= 0 for d >= 1
-                unsigned int in = ((xx0 + s00) < 1.0f ? 1u : 0u) | ((xx0 + s01) < 1.0f ? 2u : 0u) |
-                                  ((xx0 + s10) < 1.0f ? 4u : 0u) | ((xx0 + s11) < 1.0f ? 8u : 0u) |
-                                  ((xx1 + s00) < 1.0f ? 16u : 0u) | ((xx1 + s01) < 1.0f ? 32u : 0u) |
-                                  ((xx1 + s10) < 1.0f ? 64u : 0u) | ((xx1 + s11) < 1.0f ? 128u : 0u);
-                if (coarse) {
-                    const float dx = zq.x - ccx_, dy = zq.y - ccy_, dz = zq.z - ccz_;
-                    in = (in & ~cbit) | ((dx * dx + (dy * dy + dz * dz)) < 1.0f ? cbit : 0u);
-                }
-                if (q < nsurv) m |= (unsigned long long) (in & vm) << (8 * q);
+                const float d0 = xx0 + s00, d1 = xx0 + s01, d2 = xx0 + s10, d3 = xx0 + s11, d4 = xx1 + s00,
+                            d5 = xx1 + s01, d6 = xx1 + s10, d7 = xx1 + s11;
+                unsigned int in = (d0 < 1.0f ? 1u : 0u) | (d1 < 1.0f ? 2u : 0u) | (d2 < 1.0f ? 4u : 0u) |
+                                  (d3 < 1.0f ? 8u : 0u) | (d4 < 1.0f ? 16u : 0u) | (d5 < 1.0f ? 32u : 0u) |
+                                  (d6 < 1.0f ? 64u : 0u) | (d7 < 1.0f ? 128u : 0u);
+                in = q < nsurv ? (in & regular) : 0u;
+                if (in & 1u) strip[n++] = d0;
+                if (in & 2u) strip[n++] = d1;
+                if (in & 4u) strip[n++] = d2;
+                if (in & 8u) strip[n++] = d3;
+                if (in & 16u) strip[n++] = d4;
+                if (in & 32u) strip[n++] = d5;
+                if (in & 64u) strip[n++] = d6;
+                if (in & 128u) strip[n++] = d7;
+                const unsigned int sh = in << (8 * (q & 3));
+                if (q < 4) mlo |= sh; else mhi |= sh;
             }
-            const unsigned int cnt_l = (unsigned int) __popcll(m);
-            unsigned int inc = cnt_l;
+            if (any_coarse) {                       // warp-uniform: the coarse leaves' pairs follow the regular ones
+                for (int q = 0; q < max_surv; ++q) {
+                    const float4 zq = tile[q];
+                    const float dx = zq.x - ccx_, dy = zq.y - ccy_, dz = zq.z - ccz_;
+                    const float dc = dx * dx + (dy * dy + dz * dz);
+                    if (coarse && q < nsurv && dc < 1.0f) { strip[n++] = dc; mco |= 1u << q; }
+                }
+            }
+            unsigned int inc = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned int up = __shfl_up_sync(full, inc, d);
@@ -572,71 +617,46 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
             }
             const unsigned int total = __shfl_sync(full, inc, 31);
             if (total == 0) continue;
-            // the queue holds kOctQCap pairs: a tile with more is taken one point (of each block) at a time
-            const bool split = total > (unsigned int) kOctQCap;
-            const int n_parts = split ? max_surv : 1;
-            for (int part = 0; part < n_parts; ++part) {
-                unsigned long long pm = m;
-                unsigned int off = inc - cnt_l, ptotal = total;
-                if (split) {
-                    pm &= 0xFFull << (8 * part);
-                    const unsigned int c2 = (unsigned int) __popcll(pm);
-                    unsigned int i2 = c2;
+            S.inc[lane] = inc;
+            __syncwarp();
+            // ---- kernel value of every pair of the tile, all lanes busy: pair i belongs to the first lane L with inc[L] > i
+            for (unsigned int i = lane; i < total; i += 32) {
+                int L = 0;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const unsigned int up = __shfl_up_sync(full, i2, d);
-                        if (lane >= d) i2 += up;
-                    }
-                    ptotal = __shfl_sync(full, i2, 31);
-                    off = i2 - c2;
-                    if (ptotal == 0) continue;
-                }
-                // squared distances of this lane's pairs -> queue (points in order)
-                {
-                    unsigned int e = off;
-                    unsigned long long w = pm;
-                    while (w) {
-                        const int bit = __ffsll((long long) w) - 1;
-                        w &= w - 1;
-                        const int q = bit >> 3, s = bit & 7;
-                        float xc = (s & 4) ? x1 : x0, yc = (s & 2) ? y1 : y0, zc = (s & 1) ? z1 : z0;
-                        if ((cbit >> s) & 1u) { xc = ccx_; yc = ccy_; zc = ccz_; }
-                        const float4 zq = tile[q];
-                        const float dx = zq.x - xc, dy = zq.y - yc, dz = zq.z - zc;
-                        S.qd[e++] = dx * dx + (dy * dy + dz * dz);
-                    }
-                }
-                __syncwarp();
-                for (unsigned int i = lane; i < ptotal; i += 32) S.qd[i] = sparse_kernel(sqrtf(S.qd[i]), sf2);
-                __syncwarp();
-                // every lane adds its own pairs; the first pair of a new neighbour closes the previous neighbour:
-                // Occupancy::update's accumulation (bgkoctree_node.cpp:31-35) if kbar > 0 (bgkoctomap.cpp:332)
-                {
-                    unsigned int e = off;
-                    unsigned long long w = pm;
-                    while (w) {
-                        const int bit = __ffsll((long long) w) - 1;
-                        w &= w - 1;
-                        const int q = bit >> 3, s = bit & 7;
-                        const unsigned int nbq = tnb[q];
-                        const float wq = tile[q].w;
-                        const float k = S.qd[e++];
-                        float ybv = S.yb[s][lane], kbv = S.kb[s][lane];
-                        if (nbq != ((lastnb >> (4 * s)) & 0xFu)) {
-                            if (kbv > 0.0f) {
-                                S.a[s][lane] += ybv;
-                                S.b[s][lane] += kbv - ybv;
-                                touched |= 1u << s;
-                            }
-                            ybv = 0.f; kbv = 0.f;
-                            lastnb = (lastnb & ~(0xFu << (4 * s))) | (nbq << (4 * s));
-                        }
-                        S.yb[s][lane] = ybv + k * wq;
-                        S.kb[s][lane] = kbv + k;
-                    }
-                }
-                __syncwarp();
+                for (int step = 16; step > 0; step >>= 1)
+                    if (S.inc[L + step - 1] <= i) L += step;
+                const unsigned int excl = L ? S.inc[L - 1] : 0u;
+                float *pd = S.strip + L * kStripStride + (i - excl);
+                *pd = sparse_kernel(sqrtf(*pd), sf2);
             }
+            __syncwarp();
+            // ---- every lane adds its own pairs in the order it wrote them; the first pair of a new neighbour closes the
+            // previous neighbour: Occupancy::update's accumulation (bgkoctree_node.cpp:31-35) if kbar > 0
+            // (bgkoctomap.cpp:332)
+            n = 0;
+            auto add_pair = [&](int q, int sl) {
+                const unsigned int nbq = tnb[q];
+                const float wq = tile[q].w;
+                const float k = strip[n++];
+                float *col = &S.a[0][0] + sl * 32 + lane;                // a, b, yb, kb of slot sl: 256 floats apart
+                unsigned char *ln = &S.lnb[0][0] + sl * 32 + lane;
+                float ybv = col[512], kbv = col[768];
+                if (nbq != (unsigned int) *ln) {
+                    if (kbv > 0.0f) {
+                        col[0] += ybv;
+                        col[256] += kbv - ybv;
+                        touched |= 1u << sl;
+                    }
+                    ybv = 0.f; kbv = 0.f;
+                    *ln = (unsigned char) nbq;
+                }
+                col[512] = ybv + k * wq;
+                col[768] = kbv + k;
+            };
+            while (mlo) { const int bit = __ffs(mlo) - 1; mlo &= mlo - 1; add_pair(bit >> 3, bit & 7); }
+            while (mhi) { const int bit = __ffs(mhi) - 1; mhi &= mhi - 1; add_pair(4 + (bit >> 3), bit & 7); }
+            while (mco) { const int q = __ffs(mco) - 1; mco &= mco - 1; add_pair(q, cs); }
+            __syncwarp();
         }
         // ---- the last neighbour, then the rest of Occupancy::update (bgkoctree_node.cpp:36-43) once per touched leaf
 #pragma unroll
@@ -664,7 +684,6 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
         // block's 8 lanes) share FREE or OCCUPIED; node 1 + s takes child 0's floats and state (`classified` is not
         // copied, bgkoctree_node.h:40-45), the voxels become PRUNED
         unsigned int pr2 = 0, pr2_occ = 0;          // octants pruned now / as OCCUPIED (same in the block's 8 lanes)
-        const unsigned int regular = vm & ~cbit;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const unsigned int sv = ((s < 4 ? stlo : sthi) >> (8 * (s & 3))) & 7u;
@@ -894,12 +913,17 @@ void Map::enqueue_predict() {
     static const bool force_v1 = getenv("LA3DM_PREDICT_V1") != nullptr;     // debugging: the one-warp-per-block kernel
     record_event(ev_p0);
     if (hp.depth == 3 && !force_v1) {
-        static const int oct_ctas = getenv("LA3DM_OCT_CTAS") ? atoi(getenv("LA3DM_OCT_CTAS")) : 3;
-        const int n = oct_ctas == 2 ? 2 : (oct_ctas == 4 ? 4 : 3);
-        auto kern = n == 2 ? k_predict_bgk_oct<2> : (n == 4 ? k_predict_bgk_oct<4> : k_predict_bgk_oct<3>);
-        kern<<<num_sms * n, kWarpsPerCta * 32, 0, stream>>>(
+        static const int oct_ctas = getenv("LA3DM_OCT_CTAS") ? atoi(getenv("LA3DM_OCT_CTAS")) : 2;
+        const int n = oct_ctas == 1 ? 1 : 2;
+        auto kern = n == 1 ? k_predict_bgk_oct<1> : k_predict_bgk_oct<2>;
+        static bool attr_set[3] = {false, false, false};
+        if (!attr_set[n]) {
+            LA3DM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kOctSmemBytes));
+            attr_set[n] = true;
+        }
+        kern<<<num_sms * n, kWarpsPerCta * 32, kOctSmemBytes, stream>>>(
             plan.as<NeighbourPlan>(), pts_sorted.as<float4>(), keys.as<long long>(), pool.as<unsigned char>(), d_lut,
-            d_params, d_args, d_cnt);
+            d_params, d_args, d_cnt, getenv("LA3DM_OCT_NO_HEAVY") ? nullptr : heavy_list.as<unsigned int>());
     }
     else if (hp.depth <= 3)
         k_predict_bgk<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
