@@ -226,8 +226,7 @@ __global__ void k_db_place(const unsigned int *__restrict__ keys, const unsigned
         ++pos;
         const int z = (int) (id % (unsigned int) nz), y = (int) ((id / (unsigned int) nz) % (unsigned int) ny),
                   x = (int) (id / ((unsigned int) nz * (unsigned int) ny));
-        unsigned int tot = 0;
-    const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
+        const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
             const int xx = x + dx[q], yy = y + dy[q], zz = z + dz[q];

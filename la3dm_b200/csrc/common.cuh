@@ -182,7 +182,10 @@ struct ScanCounters {
     unsigned long long gp_store_needed;
 };
 
-constexpr int kTile = 2048;          // elements per CTA in the two-kernel compactions (count per tile, then place)
+#ifndef LA3DM_TILE
+#define LA3DM_TILE 512
+#endif
+constexpr int kTile = LA3DM_TILE;          // elements per CTA in the two-kernel compactions (count per tile, then place)
 constexpr int kTileThreads = 256;
 constexpr int kTileItems = kTile / kTileThreads;
 constexpr int kLongRun = 2048;       // voxel-grid runs longer than this are summed by a whole CTA each

@@ -483,14 +483,17 @@ k_hit_count(const float4 *__restrict__ hits, const ScanCounters *__restrict__ c,
 // writes the kept hits (label 1) to xy[0 .. n_hits) and every free point to frees_raw, in the reference's push order.
 // Positions come from a scan over the hits; the samples of one hit are then written by a whole warp (contiguous
 // 16-byte stores).  Sample e of a beam sits at d_e = fr + fr + ... (e fp32 additions, :451-455) = add_repeat(fr, fr, e).
-__global__ void __launch_bounds__(kHitTile)
+constexpr int kFillThreads = 1024;   // the free points of a tile are written by 4 threads per hit
+
+__global__ void __launch_bounds__(kFillThreads)
 k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__restrict__ A,
            const unsigned int *__restrict__ hit_cnt, const unsigned long long *__restrict__ tile_sums,
            unsigned int n_tiles, float4 *xy, float4 *frees, unsigned int raw_cap, unsigned int *mm_raw,
            unsigned int *mm_xy) {
     __shared__ unsigned long long smem[66];
-    __shared__ unsigned long long s_pos[kHitTile];
+    __shared__ unsigned int s_off[kHitTile];       // first free point of hit h, relative to the tile
     __shared__ unsigned int s_cnt[kHitTile];
+    __shared__ float4 s_beam[kHitTile];            // (nx, ny, nz, l) of beam_sample's preamble (:437-449)
     const unsigned int n = c->overflow ? 0u : c->n_ds_hits;
     unsigned long long prefix, total;
     block_tile_prefix(tile_sums, blockIdx.x, n_tiles, smem, prefix, total);
@@ -502,51 +505,57 @@ k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__r
     }
     if (n_raw > raw_cap) return;
     const unsigned int i = blockIdx.x * kHitTile + threadIdx.x;
-    const unsigned int cnt = i < n ? hit_cnt[i] : 0u;
+    const unsigned int cnt = (threadIdx.x < kHitTile && i < n) ? hit_cnt[i] : 0u;
     unsigned long long cta_total;
     const unsigned long long mine = cnt ? ((1ull << 32) | (unsigned long long) cnt) : 0ull;
-    s_pos[threadIdx.x] = prefix + block_exclusive_scan(mine, smem, cta_total);
-    s_cnt[threadIdx.x] = cnt;
-    __syncthreads();
+    const unsigned long long excl = block_exclusive_scan(mine, smem, cta_total);
     const float ox = A->ox, oy = A->oy, oz = A->oz, fr = A->fr;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // bounding boxes on the fly: the free samples (getMinMax3D of the second voxel grid) and the kept hits (their part
     // of the training-set bbox, src/bgkoctomap/bgkoctomap.cpp:464-484)
     float smn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, smx[3] = {-smn[0], -smn[0], -smn[0]};
     float hmn[3] = {smn[0], smn[0], smn[0]}, hmx[3] = {-smn[0], -smn[0], -smn[0]};
     bool any_s = false, any_h = false;
-    for (int h = warp; h < kHitTile; h += kHitTile / 32) {
-        const unsigned int ch = s_cnt[h];
-        if (!ch) continue;
-        const unsigned long long pos = s_pos[h];
-        const float4 hit = hits[blockIdx.x * kHitTile + h];
-        float4 *out = frees + (unsigned int) (pos & 0xFFFFFFFFull);
-        if (lane == 0) {
-            xy[(unsigned int) (pos >> 32)] = make_float4(hit.x, hit.y, hit.z, 1.0f);       // :399
-            out[0] = make_float4(ox, oy, oz, 0.f);                                        // :404
-            hmn[0] = fminf(hmn[0], hit.x); hmx[0] = fmaxf(hmx[0], hit.x);
-            hmn[1] = fminf(hmn[1], hit.y); hmx[1] = fmaxf(hmx[1], hit.y);
-            hmn[2] = fminf(hmn[2], hit.z); hmx[2] = fmaxf(hmx[2], hit.z);
-            smn[0] = fminf(smn[0], ox); smx[0] = fmaxf(smx[0], ox);
-            smn[1] = fminf(smn[1], oy); smx[1] = fmaxf(smx[1], oy);
-            smn[2] = fminf(smn[2], oz); smx[2] = fmaxf(smx[2], oz);
-            any_h = any_s = true;
-        }
-        // beam_sample preamble (:437-449)
+    // ---- one thread per hit: the kept hit itself (:399) and its beam's direction and length
+    if (threadIdx.x < kHitTile) {
+        s_off[threadIdx.x] = (unsigned int) (excl & 0xFFFFFFFFull);
+        s_cnt[threadIdx.x] = cnt;
+    }
+    if (cnt) {
+        const float4 hit = hits[i];
+        xy[(unsigned int) ((prefix + excl) >> 32)] = make_float4(hit.x, hit.y, hit.z, 1.0f);
+        hmn[0] = hmx[0] = hit.x; hmn[1] = hmx[1] = hit.y; hmn[2] = hmx[2] = hit.z;
+        any_h = true;
         const float dx = hit.x - ox, dy = hit.y - oy, dz = hit.z - oz;
         const float l = (float) sqrt((double) (dx * dx + dy * dy + dz * dz));
-        const float nx = dx / l, ny = dy / l, nz = dz / l;
-        const unsigned int tail = l > fr ? 1u : 0u;
-        const unsigned int n_reg = ch - 1u - tail;                                        // samples with d < l (:451-455)
-        for (unsigned int e = lane; e < ch - 1u; e += 32) {
-            const float d = e < n_reg ? (e < A->beam_tab_n ? A->beam_tab[e] : add_repeat(fr, fr, e)) : l - fr;   // :453 | :457
-            const float sx = ox + nx * d, sy = oy + ny * d, sz = oz + nz * d;
-            out[1 + e] = make_float4(sx, sy, sz, 0.f);
-            smn[0] = fminf(smn[0], sx); smx[0] = fmaxf(smx[0], sx);
-            smn[1] = fminf(smn[1], sy); smx[1] = fmaxf(smx[1], sy);
-            smn[2] = fminf(smn[2], sz); smx[2] = fmaxf(smx[2], sz);
-            any_s = true;
+        s_beam[threadIdx.x] = make_float4(dx / l, dy / l, dz / l, l);
+    }
+    __syncthreads();
+    // ---- one thread per free point of the tile, in the reference's push order (origin :404, samples :451-457):
+    // the hit is the last one whose first free point is <= j (hits that emit nothing share their successor's offset)
+    const unsigned int tile_frees = (unsigned int) (cta_total & 0xFFFFFFFFull);
+    float4 *out = frees + (unsigned int) (prefix & 0xFFFFFFFFull);
+    const unsigned int tab_n = A->beam_tab_n;
+    const float *__restrict__ tab = A->beam_tab;
+    for (unsigned int j = threadIdx.x; j < tile_frees; j += kFillThreads) {
+        unsigned int h = 0;
+#pragma unroll
+        for (unsigned int step = kHitTile / 2; step > 0; step >>= 1)
+            if (s_off[h + step] <= j) h += step;
+        const unsigned int e1 = j - s_off[h];
+        float sx = ox, sy = oy, sz = oz;
+        if (e1) {
+            const unsigned int e = e1 - 1u, ch = s_cnt[h];
+            const float4 bm = s_beam[h];
+            const unsigned int tail = bm.w > fr ? 1u : 0u;
+            const unsigned int n_reg = ch - 1u - tail;                                    // samples with d < l (:451-455)
+            const float d = e < n_reg ? (e < tab_n ? tab[e] : add_repeat(fr, fr, e)) : bm.w - fr;   // :453 | :457
+            sx = ox + bm.x * d; sy = oy + bm.y * d; sz = oz + bm.z * d;
         }
+        out[j] = make_float4(sx, sy, sz, 0.f);
+        smn[0] = fminf(smn[0], sx); smx[0] = fmaxf(smx[0], sx);
+        smn[1] = fminf(smn[1], sy); smx[1] = fmaxf(smx[1], sy);
+        smn[2] = fminf(smn[2], sz); smx[2] = fmaxf(smx[2], sz);
+        any_s = true;
     }
     warp_minmax_box(any_s, smn, smx, mm_raw);
     warp_minmax_box(any_h, hmn, hmx, mm_xy);
@@ -627,7 +636,7 @@ void Map::enqueue_frontend_bgk() {
     unsigned long long *tile_sums = tiles.as<unsigned long long>();
     k_hit_count<<<n_tiles, kHitTile, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
                                                   tile_sums);
-    k_hit_fill<<<n_tiles, kHitTile, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
+    k_hit_fill<<<n_tiles, kFillThreads, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, hit_cnt.as<unsigned int>(),
                                                  tile_sums, (unsigned int) n_tiles, xy.as<float4>(),
                                                  frees_raw.as<float4>(), caps.raw, d_mm + 6, d_mm + 12);
     launches += 2;
