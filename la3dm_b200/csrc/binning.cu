@@ -22,36 +22,64 @@ constexpr unsigned int kPad = 0xFFFFFFFFu;
 // that write xy: k_hit_fill, k_vg_centroid<1>, k_vg_long<1>)
 
 // ---- block grid of the scan (get_blocks_in_bbox, :486-495); *g was zeroed by a memset ------------------------------
-__global__ void k_grid(const unsigned int *__restrict__ mm, const DevParams *__restrict__ P, GridDesc *g,
-                       ScanCounters *c, unsigned int cells_cap) {
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) s_bad = 0;
-    __syncthreads();
+// Three groups of 128 threads, one per axis.  The stepping  x += block_size  is a chain of dependent fp32 additions and
+// stays sequential (one thread per axis writes the positions to shared memory, kGridChunk at a time); the block index of
+// every position (a double division) and the bookkeeping are done by the whole group.
+constexpr int kGridChunk = 2048;
+constexpr int kGridThreads = 384;
+
+__global__ void __launch_bounds__(kGridThreads)
+k_grid(const unsigned int *__restrict__ mm, const DevParams *__restrict__ P, GridDesc *g, ScanCounters *c,
+       unsigned int cells_cap) {
+    __shared__ float xs[3][kGridChunk];
+    __shared__ float s_x[3];
+    __shared__ long long s_last[3];
+    __shared__ int s_cnt[3], s_steps[3], s_done[3], s_bad, s_irr;
     const bool live = !c->overflow && c->n_train > 0;
-    const int a = threadIdx.x;
+    const int a = threadIdx.x >> 7, t = threadIdx.x & 127;
     const float bs = P->block_size;
-    if (live && a < 3) {
-        const float mn = float_unflip(mm[a]), mx = float_unflip(mm[3 + a]);
-        long long first = 0, prev = 0;
-        int steps = 0, irregular = 0, bad = 0;
-        const float hi = mx + 2 * bs;
-        for (float x = mn - bs; x <= hi; x += bs) {
-            const long long idx = axis_index(x, bs);
-            if (steps == 0) first = idx;
-            else if (idx != prev + 1) irregular = 1;
-            const long long rel = idx - first;
-            if (rel < 0 || rel >= kMaxAxis || steps >= kMaxAxis) { bad = 1; break; }
-            g->present[a][rel] = 1;
-            prev = idx;
-            ++steps;
+    const float mn = float_unflip(mm[a]), mx = float_unflip(mm[3 + a]);
+    const float hi = mx + 2 * bs;
+    const long long first = axis_index(mn - bs, bs);
+    if (threadIdx.x == 0) { s_bad = 0; s_irr = 0; }
+    if (t == 0) { s_x[a] = mn - bs; s_steps[a] = 0; s_done[a] = live ? 0 : 1; s_last[a] = first - 1; }
+    __syncthreads();
+    while (!(s_done[0] && s_done[1] && s_done[2]) && !s_bad) {
+        if (t == 0) {
+            int n = 0;
+            if (!s_done[a]) {
+                float x = s_x[a];
+                while (n < kGridChunk && x <= hi) { xs[a][n++] = x; x += bs; }
+                s_x[a] = x;
+            }
+            s_cnt[a] = n;
         }
+        __syncthreads();
+        const int n = s_cnt[a], base = s_steps[a];
+        const long long last_before = s_last[a];
+        __syncthreads();
+        for (int j = t; j < n; j += 128) {
+            const long long idx = axis_index(xs[a][j], bs);
+            const long long prev = j ? axis_index(xs[a][j - 1], bs) : last_before;
+            if (base + j > 0 && idx != prev + 1) s_irr = 1;
+            const long long rel = idx - first;
+            if (rel < 0 || rel >= kMaxAxis || base + j >= kMaxAxis) s_bad = 1;
+            else g->present[a][rel] = 1;
+            if (j == n - 1) s_last[a] = idx;
+        }
+        if (t == 0) {
+            s_steps[a] = base + n;
+            if (n < kGridChunk) s_done[a] = 1;          // the stepping passed max + 2 block_size
+        }
+        __syncthreads();
+    }
+    if (live && t == 0) {
         g->base[a] = first;
-        g->n[a] = steps == 0 ? 0 : (int) (prev - first + 1);
-        if (irregular) atomicOr(&g->irregular, 1);
-        if (bad) atomicOr(&s_bad, 1);
+        g->n[a] = s_steps[a] == 0 ? 0 : (int) (s_last[a] - first + 1);
     }
     __syncthreads();
-    if (live && a == 0) {
+    if (live && threadIdx.x == 0) {
+        if (s_irr) g->irregular = 1;
         const unsigned long long cells = (unsigned long long) g->n[0] * (unsigned long long) g->n[1] *
                                          (unsigned long long) g->n[2];
         if (s_bad || cells >= 0x7FFFFFF0ull) atomicOr(&c->overflow, OVF_EXTENT);
@@ -409,7 +437,7 @@ void Map::ensure_pool(size_t blocks) {
 // the float-stepped block grid of the scan from the bounding box of the training set (d_mm + 12)
 void Map::enqueue_block_grid() {
     LA3DM_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(GridDesc), stream));
-    k_grid<<<1, 32, 0, stream>>>(d_mm + 12, d_params, d_grid, d_cnt, caps.cells);
+    k_grid<<<1, kGridThreads, 0, stream>>>(d_mm + 12, d_params, d_grid, d_cnt, caps.cells);
     ++launches;
 }
 

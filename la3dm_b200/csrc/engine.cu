@@ -127,7 +127,7 @@ __global__ void k_leaf_total(const unsigned int *__restrict__ cnt, const unsigne
 }
 
 unsigned int grow_to(unsigned int need, unsigned int floor_) {
-    const unsigned long long w = (unsigned long long) need + need / 4 + 64;
+    const unsigned long long w = (unsigned long long) need + need / 8 + 64;
     return (unsigned int) std::min<unsigned long long>(std::max<unsigned long long>(w, floor_), 0x7FFFFFF0ull);
 }
 

@@ -262,6 +262,19 @@ __global__ void k_vg_centroid(const ScanArgs *__restrict__ A, ScanCounters *c, c
 // repeated-point sub-chunks are added with ONE add_repeat (exact, no loads), anything else is staged through shared
 // memory and added element by element by three lanes (x, y, z).  Medium runs get one warp each.
 constexpr int kLongThreads = 512;
+
+// acc + v[0] + v[1] + ... + v[m - 1], added one by one in that order (pcl's CentroidPoint); v is 16-byte aligned shared
+// memory, read eight values ahead of the dependent chain of additions
+__device__ __forceinline__ float seq_sum(float acc, const float *v, unsigned int m) {
+    unsigned int j = 0;
+    for (; j + 8 <= m; j += 8) {
+        const float4 a = *reinterpret_cast<const float4 *>(v + j), b = *reinterpret_cast<const float4 *>(v + j + 4);
+        acc += a.x; acc += a.y; acc += a.z; acc += a.w;
+        acc += b.x; acc += b.y; acc += b.z; acc += b.w;
+    }
+    for (; j < m; ++j) acc += v[j];
+    return acc;
+}
 constexpr int kSub = 256;                      // points per sub-chunk (8 per lane)
 constexpr int kMidSub = 128;                   // points a warp stages at a time for a medium run
 constexpr int kSubsPerPass = 1024;             // sub-chunk flags staged in shared memory at a time
@@ -315,8 +328,8 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
           const unsigned char *__restrict__ lf_same, unsigned int n_sub_cap, unsigned int *mm_xy) {
     __shared__ float first[kSubsPerPass][3];   // the sub-chunk's first point
     __shared__ unsigned char same[kSubsPerPass];
-    __shared__ float stage[3][kSub];
-    __shared__ float wstage[kLongThreads / 32][3][kMidSub];
+    __shared__ __align__(16) float stage[3][kSub];
+    __shared__ __align__(16) float wstage[kLongThreads / 32][3][kMidSub];
     if (c->overflow) return;
     const unsigned int nl = min(c->n_long_runs[W], (unsigned int) kMaxLongRuns);
     const unsigned int nm = min(c->n_mid_runs[W], (unsigned int) kMaxMidRuns);
@@ -330,22 +343,30 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
         const unsigned int r = long_list[kMaxLongRuns + idx];
         const unsigned int run_first = run_start[r], run_last = run_start[r + 1];
         float acc = 0.f;
+        float px[kMidSub / 32], py[kMidSub / 32], pz[kMidSub / 32];
+        auto fetch = [&](unsigned int s0) {
+            const unsigned int m = min((unsigned int) kMidSub, run_last - s0);
+#pragma unroll
+            for (int k = 0; k < kMidSub / 32; ++k) {
+                const unsigned int j = lane + 32 * k;
+                if (j < m) {
+                    const float *p = in + (size_t) vals[s0 + j] * stride;
+                    px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+                }
+            }
+        };
+        fetch(run_first);
         for (unsigned int s0 = run_first; s0 < run_last; s0 += kMidSub) {
             const unsigned int m = min((unsigned int) kMidSub, run_last - s0);
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < kMidSub / 32; ++k) {
                 const unsigned int j = lane + 32 * k;
-                if (j < m) {
-                    const float *p = in + (size_t) vals[s0 + j] * stride;
-                    wstage[warp][0][j] = p[0]; wstage[warp][1][j] = p[1]; wstage[warp][2][j] = p[2];
-                }
+                if (j < m) { wstage[warp][0][j] = px[k]; wstage[warp][1][j] = py[k]; wstage[warp][2][j] = pz[k]; }
             }
             __syncwarp();
-            if (lane < 3) {
-                const float *v = wstage[warp][lane];
-                for (unsigned int j = 0; j < m; ++j) acc += v[j];
-            }
+            if (s0 + kMidSub < run_last) fetch(s0 + kMidSub);     // in flight while three lanes add this chunk
+            if (lane < 3) acc = seq_sum(acc, wstage[warp][lane], m);
         }
         float *o = reinterpret_cast<float *>(out + off + r);
         if (lane < 3) {
@@ -355,7 +376,8 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
         } else if (lane == 3) o[3] = label;
     }
     // ---- long runs: one CTA each
-    for (unsigned int idx = blockIdx.x; idx < nl; idx += gridDim.x) {
+    // (dealt from the last CTA backwards: the medium runs above fill the first CTAs)
+    for (unsigned int idx = gridDim.x - 1 - blockIdx.x; idx < nl; idx += gridDim.x) {
         const unsigned int r = long_list[idx];
         const unsigned int run_first = run_start[r], run_last = run_start[r + 1];
         const unsigned int g0 = min((run_first + kSub - 1) / kSub, n_sub_cap), g1 = min(run_last / kSub, n_sub_cap);
@@ -392,10 +414,7 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
                             stage[0][threadIdx.x] = p[0]; stage[1][threadIdx.x] = p[1]; stage[2][threadIdx.x] = p[2];
                         }
                         __syncthreads();
-                        if (threadIdx.x < 3) {
-                            const float *v = stage[threadIdx.x];
-                            for (unsigned int j = 0; j < (unsigned int) kSub; ++j) acc += v[j];
-                        }
+                        if (threadIdx.x < 3) acc = seq_sum(acc, stage[threadIdx.x], (unsigned int) kSub);
                         __syncthreads();
                     }
                 }
@@ -410,10 +429,7 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
                     stage[0][threadIdx.x] = p[0]; stage[1][threadIdx.x] = p[1]; stage[2][threadIdx.x] = p[2];
                 }
                 __syncthreads();
-                if (threadIdx.x < 3) {
-                    const float *v = stage[threadIdx.x];
-                    for (unsigned int j = 0; j < m; ++j) acc += v[j];
-                }
+                if (threadIdx.x < 3) acc = seq_sum(acc, stage[threadIdx.x], m);
                 __syncthreads();
                 pos += m;
             }
@@ -440,13 +456,14 @@ __device__ inline unsigned int hit_free_count(const float4 h, const ScanArgs *A)
     }
     const float l = (float) sqrt((double) s);
     const float fr = A->fr;
-    // number of e with beam_tab[e] < l (the table is non-decreasing); beyond the table continue the accumulation
+    // number of e with beam_tab[e] < l (the table is non-decreasing, beam_tab[e] ~ (e + 1) fr): start from the estimate
+    // l / fr and walk to the exact boundary; beyond the table continue the accumulation
     const float *__restrict__ tab = A->beam_tab;
-    unsigned int lo = 0, hi = A->beam_tab_n;
-    while (lo < hi) {
-        const unsigned int mid = (lo + hi) >> 1;
-        if (tab[mid] < l) lo = mid + 1; else hi = mid;
-    }
+    const unsigned int tab_n = A->beam_tab_n;
+    const float est = l / fr;
+    unsigned int lo = est < (float) tab_n ? (unsigned int) est : tab_n;
+    while (lo < tab_n && tab[lo] < l) ++lo;
+    while (lo > 0 && !(tab[lo - 1] < l)) --lo;
     unsigned int cnt = 1 + lo;                              // the origin + regular samples
     if (lo == A->beam_tab_n) {
         float d = tab[lo - 1] + fr;
@@ -483,7 +500,7 @@ k_hit_count(const float4 *__restrict__ hits, const ScanCounters *__restrict__ c,
 // writes the kept hits (label 1) to xy[0 .. n_hits) and every free point to frees_raw, in the reference's push order.
 // Positions come from a scan over the hits; the samples of one hit are then written by a whole warp (contiguous
 // 16-byte stores).  Sample e of a beam sits at d_e = fr + fr + ... (e fp32 additions, :451-455) = add_repeat(fr, fr, e).
-constexpr int kFillThreads = 1024;   // the free points of a tile are written by 4 threads per hit
+constexpr int kFillThreads = 4 * 256;   // = 4 * kHitTile: the free points of a hit are written by 4 threads
 
 __global__ void __launch_bounds__(kFillThreads)
 k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__restrict__ A,
@@ -530,32 +547,32 @@ k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__r
         s_beam[threadIdx.x] = make_float4(dx / l, dy / l, dz / l, l);
     }
     __syncthreads();
-    // ---- one thread per free point of the tile, in the reference's push order (origin :404, samples :451-457):
-    // the hit is the last one whose first free point is <= j (hits that emit nothing share their successor's offset)
-    const unsigned int tile_frees = (unsigned int) (cta_total & 0xFFFFFFFFull);
+    // ---- four threads per hit write its free points in the reference's push order (origin :404, samples :451-457)
+    (void) cta_total;
     float4 *out = frees + (unsigned int) (prefix & 0xFFFFFFFFull);
     const unsigned int tab_n = A->beam_tab_n;
     const float *__restrict__ tab = A->beam_tab;
-    for (unsigned int j = threadIdx.x; j < tile_frees; j += kFillThreads) {
-        unsigned int h = 0;
-#pragma unroll
-        for (unsigned int step = kHitTile / 2; step > 0; step >>= 1)
-            if (s_off[h + step] <= j) h += step;
-        const unsigned int e1 = j - s_off[h];
-        float sx = ox, sy = oy, sz = oz;
-        if (e1) {
-            const unsigned int e = e1 - 1u, ch = s_cnt[h];
+    {
+        const unsigned int h = threadIdx.x >> 2, ch = s_cnt[h];
+        if (ch) {
+            const unsigned int first = s_off[h];
             const float4 bm = s_beam[h];
             const unsigned int tail = bm.w > fr ? 1u : 0u;
             const unsigned int n_reg = ch - 1u - tail;                                    // samples with d < l (:451-455)
-            const float d = e < n_reg ? (e < tab_n ? tab[e] : add_repeat(fr, fr, e)) : bm.w - fr;   // :453 | :457
-            sx = ox + bm.x * d; sy = oy + bm.y * d; sz = oz + bm.z * d;
+            for (unsigned int e1 = threadIdx.x & 3u; e1 < ch; e1 += 4u) {
+                float sx = ox, sy = oy, sz = oz;
+                if (e1) {
+                    const unsigned int e = e1 - 1u;
+                    const float d = e < n_reg ? (e < tab_n ? tab[e] : add_repeat(fr, fr, e)) : bm.w - fr;   // :453 | :457
+                    sx = ox + bm.x * d; sy = oy + bm.y * d; sz = oz + bm.z * d;
+                }
+                out[first + e1] = make_float4(sx, sy, sz, 0.f);
+                smn[0] = fminf(smn[0], sx); smx[0] = fmaxf(smx[0], sx);
+                smn[1] = fminf(smn[1], sy); smx[1] = fmaxf(smx[1], sy);
+                smn[2] = fminf(smn[2], sz); smx[2] = fmaxf(smx[2], sz);
+                any_s = true;
+            }
         }
-        out[j] = make_float4(sx, sy, sz, 0.f);
-        smn[0] = fminf(smn[0], sx); smx[0] = fmaxf(smx[0], sx);
-        smn[1] = fminf(smn[1], sy); smx[1] = fmaxf(smx[1], sy);
-        smn[2] = fminf(smn[2], sz); smx[2] = fmaxf(smx[2], sz);
-        any_s = true;
     }
     warp_minmax_box(any_s, smn, smx, mm_raw);
     warp_minmax_box(any_h, hmn, hmx, mm_xy);
