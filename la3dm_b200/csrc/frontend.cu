@@ -32,6 +32,8 @@ __global__ void k_scan_begin(ScanCounters *c, unsigned int *mm) {
     if (threadIdx.x < 18) mm[threadIdx.x] = (threadIdx.x % 6) < 3 ? 0xFFFFFFFFu : 0u;   // flipped min | max
 }
 
+__device__ inline void block_minmax_box(bool valid, float *mn, float *mx, unsigned int *mm, unsigned int *s_mm);
+
 __device__ inline void minmax_accumulate(const float *__restrict__ in, int stride, unsigned int n, unsigned int *mm) {
     float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
     float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
@@ -42,21 +44,8 @@ __device__ inline void minmax_accumulate(const float *__restrict__ in, int strid
         for (int a = 0; a < 3; ++a) { const float v = p[a]; mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v); }
         any = true;
     }
-    if (!__any_sync(0xffffffffu, any)) return;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
-        }
-    }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMin(&mm[a], float_flip(mn[a]));
-            atomicMax(&mm[3 + a], float_flip(mx[a]));
-        }
-    }
+    __shared__ unsigned int s_mm[6];
+    block_minmax_box(any, mn, mx, mm, s_mm);
 }
 
 // warp-level min/max of one point per lane into mm[0..2] (min) / mm[3..5] (max), flipped-uint encoding.
@@ -98,6 +87,18 @@ __device__ inline void warp_minmax_box(bool valid, float *mn, float *mx, unsigne
             atomicMax(&mm[3 + a], float_flip(mx[a]));
         }
     }
+}
+
+// CTA-level version: warps combine in shared memory (s_mm: 6 words), then ONE set of global atomics per CTA -- thousands
+// of warps hitting the same six addresses serialise in L2.  Every thread of the CTA must call it.
+__device__ inline void block_minmax_box(bool valid, float *mn, float *mx, unsigned int *mm, unsigned int *s_mm) {
+    if (threadIdx.x < 6) s_mm[threadIdx.x] = threadIdx.x < 3 ? 0xFFFFFFFFu : 0u;
+    __syncthreads();
+    warp_minmax_box(valid, mn, mx, s_mm);
+    __syncthreads();
+    if (threadIdx.x < 3) { if (s_mm[threadIdx.x] != 0xFFFFFFFFu) atomicMin(&mm[threadIdx.x], s_mm[threadIdx.x]); }
+    else if (threadIdx.x < 6) { if (s_mm[threadIdx.x] != 0u) atomicMax(&mm[threadIdx.x], s_mm[threadIdx.x]); }
+    __syncthreads();
 }
 
 // getMinMax3D of a voxel-grid input
@@ -574,8 +575,9 @@ k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__r
             }
         }
     }
-    warp_minmax_box(any_s, smn, smx, mm_raw);
-    warp_minmax_box(any_h, hmn, hmx, mm_xy);
+    __shared__ unsigned int s_mm[6];
+    block_minmax_box(any_s, smn, smx, mm_raw, s_mm);
+    block_minmax_box(any_h, hmn, hmx, mm_xy, s_mm);
 }
 
 __global__ void k_finish_train(ScanCounters *c) {
