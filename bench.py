@@ -389,7 +389,7 @@ def run_ours(a):
                     "api": "la3dm_insert_pointcloud (pinned host cloud) + la3dm_last_stats"},
             "gpu_launches": int(sum(st_d[s]["kernel_launches"] for s in timed)),
             "collectives_per_step": st_d[timed[0]]["collectives"],
-            "roofline": {"kernel": "k_predict_bgk (fused predict + Occupancy::update + prune)", "bound": "hbm",
+            "roofline": {"kernel": "k_predict_bgk_oct (fused predict + Occupancy::update + prune)", "bound": "hbm",
                          "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                          "kernel_share_of_step": k_ms / (1e3 * T / a.steps), "algorithmic_bytes": k_bytes,
