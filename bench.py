@@ -222,7 +222,7 @@ def run_reference(a):
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -426,13 +426,35 @@ def run_ours(a):
                                               "(oracle/_ref fast flavour: the reference's own sources, -O3 AVX2, OpenMP)"
                                               % (ns - 1),
                                     "ms_per_scan": 1e3 * sum(secs) / len(secs), "host_cpus": os.cpu_count()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The driver parses ONE JSON line from stdout: send everything else written to fd 1 (NCCL's version banner, library
+    chatter from any rank) to stderr and keep a private handle on the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

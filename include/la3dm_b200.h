@@ -172,6 +172,27 @@ int la3dm_export_blocks(la3dm_map *map, int64_t *keys, la3dm_node *nodes, size_t
 int64_t la3dm_num_leaves(la3dm_map *map);
 int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t *n_out);
 
+/* Point query, batched: replaces  OcTreeNode search(point3f p) / search(float x, float y, float z)
+ * (include/bgkoctomap/bgkoctomap.h:315-319; src/bgkoctomap/bgkoctomap.cpp:554-574 -> Block::search,
+ * src/bgkoctomap/bgkblock.cpp:132-156).  xyz: HOST pointer, n points, stride_bytes per record; out: n HOST records.
+ * out[i] describes the node that holds point i: block_key = block_to_hash_key(p); a block that does not exist answers
+ * like upstream's `return OcTreeNode()` (default node) with depth = index = -1.  finest_only != 0 returns the
+ * finest-layer node of the point's cell even when it is PRUNED (what upstream's operator[] hands back); 0 returns the
+ * LEAF containing the point.  The cell index uses cell_num = 2^(block_depth-1): upstream freezes Block::cell_num at 8
+ * during static initialisation (bgkblock.cpp:105), which is only right for block_depth 4. */
+int la3dm_search(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, int finest_only, la3dm_leaf *out);
+
+/* Inverse of la3dm_export_blocks: fills an EMPTY map from HOST arrays in the reference's Block/OcTree layout
+ * (keys[i], nodes[i * nodes_per_block + ...]); afterwards scans can be inserted as if the map had been built here. */
+int la3dm_import_blocks(la3dm_map *map, const int64_t *keys, const la3dm_node *nodes, size_t n_blocks);
+
+/* Map serialisation / checkpoint (the reference only has the unused node stream operators,
+ * src/bgkoctomap/bgkoctree_node.cpp:46-58).  File = header (magic, method, la3dm_params) + sorted block keys + node
+ * arrays as la3dm_export_blocks returns them.  la3dm_load needs an EMPTY map created with the same method and
+ * parameters (LA3DM_ERR_INVALID otherwise). */
+int la3dm_save(la3dm_map *map, const char *path);
+int la3dm_load(la3dm_map *map, const char *path);
+
 /* get_bbox() (src/bgkoctomap/bgkoctomap.cpp:368-381). */
 int la3dm_get_bbox(la3dm_map *map, float lim_min[3], float lim_max[3]);
 

@@ -61,6 +61,9 @@ struct vec3f {
 class OcTreeNode {
 public:
     explicit OcTreeNode(const la3dm_leaf *l = nullptr) : l_(l) {}
+    explicit OcTreeNode(const la3dm_leaf &copy) : own_(copy), l_(&own_) {}
+    OcTreeNode(const OcTreeNode &o) : own_(o.own_), l_(o.l_ == &o.own_ ? &own_ : o.l_) {}
+    OcTreeNode &operator=(const OcTreeNode &o) { own_ = o.own_; l_ = o.l_ == &o.own_ ? &own_ : o.l_; return *this; }
     float get_prob() const { return l_ ? l_->prob : 0.5f; }
     float get_var() const { return l_ ? l_->var : 0.f; }
     State get_state() const { return l_ ? static_cast<State>(l_->state) : State::UNKNOWN; }
@@ -69,6 +72,7 @@ public:
     float get_a() const { return l_ ? l_->a : 0.f; }   /* m_A | GP m_ivar */
     float get_b() const { return l_ ? l_->b : 0.f; }   /* m_B | GP ivar   */
 private:
+    la3dm_leaf own_ = la3dm_leaf();
     const la3dm_leaf *l_;
 };
 
@@ -150,21 +154,22 @@ public:
     LeafIterator end_leaf() const { refresh(); return LeafIterator(this, leaves_.size()); }
     size_t num_leaves() const { refresh(); return leaves_.size(); }
 
-    /// search(x, y, z): the leaf whose cube holds the point (an UNKNOWN default node if the block does not exist).
+    /// search(x, y, z) (include/bgkoctomap/bgkoctomap.h:315-319): the leaf that holds the point, looked up on the
+    /// device (la3dm_search); an UNKNOWN default node if the block does not exist, like upstream's `OcTreeNode()`.
     /// The reference's Block::search is only right for block_depth 4; this one is right for any depth.
     OcTreeNode search(float x, float y, float z) const {
-        refresh();
-        const BlockHashKey key = la3dm_block_to_hash_key(h_, x, y, z);
-        auto it = block_range_.find(key);
-        if (it == block_range_.end()) return OcTreeNode();
-        for (size_t i = it->second.first; i < it->second.second; ++i) {
-            const la3dm_leaf &l = leaves_[i];
-            const float h = l.size * 0.5f;
-            if (x >= l.x - h && x <= l.x + h && y >= l.y - h && y <= l.y + h && z >= l.z - h && z <= l.z + h)
-                return OcTreeNode(&l);
-        }
-        return OcTreeNode();
+        const float q[3] = {x, y, z};
+        la3dm_leaf l;
+        check(la3dm_search(h_, q, 1, sizeof(q), 0, &l));
+        return l.depth < 0 ? OcTreeNode() : OcTreeNode(l);
     }
+    /// batch form: n points (x y z at the start of each stride_bytes record) -> n leaf records (depth -1: no block)
+    void search(const float *xyz, size_t n, size_t stride_bytes, la3dm_leaf *out, bool finest_only = false) const {
+        check(la3dm_search(h_, xyz, n, stride_bytes, finest_only ? 1 : 0, out));
+    }
+    /// checkpoint / resume (la3dm_save / la3dm_load; load needs an empty map with the same parameters)
+    void save(const std::string &path) const { check(la3dm_save(h_, path.c_str())); }
+    void load(const std::string &path) { check(la3dm_load(h_, path.c_str())); dirty_ = true; }
     template <class Point>
     OcTreeNode search(const Point &p) const { return search(p.x(), p.y(), p.z()); }
 

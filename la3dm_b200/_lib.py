@@ -62,6 +62,10 @@ SYMBOLS = {
     "la3dm_export_blocks": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "la3dm_num_leaves": (C.c_int64, [_P]),
     "la3dm_export_leaves": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "la3dm_search": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, _P]),
+    "la3dm_import_blocks": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "la3dm_save": (C.c_int, [_P, C.c_char_p]),
+    "la3dm_load": (C.c_int, [_P, C.c_char_p]),
     "la3dm_get_bbox": (C.c_int, [_P, _P, _P]),
     "la3dm_block_to_hash_key": (C.c_int64, [_P, C.c_float, C.c_float, C.c_float]),
     "la3dm_hash_key_to_block": (None, [_P, C.c_int64, _P]),

@@ -183,6 +183,26 @@ int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t
     return guarded(map, [&] { map->m.export_leaves(out, capacity, n_out); });
 }
 
+int la3dm_search(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, int finest_only, la3dm_leaf *out) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] { map->m.search(xyz, n, stride_bytes, false, finest_only, out); });
+}
+
+int la3dm_import_blocks(la3dm_map *map, const int64_t *keys, const la3dm_node *nodes, size_t n_blocks) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] { map->m.import_blocks(keys, nodes, n_blocks); });
+}
+
+int la3dm_save(la3dm_map *map, const char *path) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] { map->m.save(path); });
+}
+
+int la3dm_load(la3dm_map *map, const char *path) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] { map->m.load(path); });
+}
+
 int64_t la3dm_block_to_hash_key(const la3dm_map *map, float x, float y, float z) {
     if (!map) return -1;
     const float bs = map->m.hp.block_size;

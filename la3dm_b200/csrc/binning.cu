@@ -9,6 +9,7 @@
 #include <cub/cub.cuh>
 
 #include "engine.cuh"
+#include "hash.cuh"
 #include "runs.cuh"
 
 namespace la3dm_b200 {
@@ -323,27 +324,6 @@ __global__ void k_test_place(const unsigned int *__restrict__ bits, unsigned int
 }
 
 // ---- persistent block map -----------------------------------------------------------------------------------------
-__device__ inline int hash_find(const long long *__restrict__ hkeys, const int *__restrict__ hvals, size_t mask,
-                                long long key) {
-    size_t h = (size_t) mix64((unsigned long long) key) & mask;
-    while (true) {
-        const long long k = hkeys[h];
-        if (k == key) return hvals[h];
-        if (k == -1) return -1;
-        h = (h + 1) & mask;
-    }
-}
-
-__device__ inline void hash_insert(long long *hkeys, int *hvals, size_t mask, long long key, int val) {
-    size_t h = (size_t) mix64((unsigned long long) key) & mask;
-    while (true) {
-        const unsigned long long prev = atomicCAS((unsigned long long *) &hkeys[h], (unsigned long long) -1LL,
-                                                  (unsigned long long) key);
-        if (prev == (unsigned long long) -1LL || prev == (unsigned long long) key) { hvals[h] = val; return; }
-        h = (h + 1) & mask;
-    }
-}
-
 // One thread per test block: find or create its slot in the map, and look up the training ranges of its 7 neighbours
 // [self,+x,-x,+y,-y,+z,-z] (src/bgkoctomap/bgkblock.cpp:85-101) through the cell -> data block table.
 // This is the first kernel of the scan that touches the persistent map; every capacity check has been made by now.
@@ -434,6 +414,14 @@ void Map::ensure_pool(size_t blocks) {
                 keys.as<long long>(), (unsigned int) n_blocks, hkeys.as<long long>(), hvals.as<int>(), need - 1);
         invalidate_graph();
     }
+}
+
+// key -> slot table from scratch over keys[0 .. n_blocks) (after an import)
+void Map::rebuild_hash() {
+    k_hash_clear<<<ceil_div((long long) hash_cap, kThreads), kThreads, 0, stream>>>(hkeys.as<long long>(), hash_cap);
+    if (n_blocks > 0)
+        k_hash_rebuild<<<ceil_div(n_blocks, kThreads), kThreads, 0, stream>>>(
+            keys.as<long long>(), (unsigned int) n_blocks, hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1);
 }
 
 // the float-stepped block grid of the scan from the bounding box of the training set (d_mm + 12)

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "engine.cuh"
+#include "leaf.cuh"
 
 namespace la3dm_b200 {
 
@@ -37,13 +38,6 @@ __global__ void k_gather_keys(const long long *__restrict__ keys, const unsigned
                               unsigned int n, long long *out) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = keys[order[i]];
-}
-
-// is_leaf (src/bgkoctomap/bgkoctree.cpp:72-82) on the packed state bytes
-__device__ inline bool node_is_leaf(const unsigned char *bst, const DevParams &P, int d, int i) {
-    if ((bst[P.layer_off[d] + i] & 7) == P.pruned_state) return false;
-    if (d + 1 < P.depth) return (bst[P.layer_off[d + 1] + 8 * i] & 7) == P.pruned_state;
-    return true;
 }
 
 __global__ void k_leaf_count(const unsigned char *__restrict__ pool, const unsigned int *__restrict__ order,
@@ -89,31 +83,7 @@ __global__ void k_leaf_fill(const unsigned char *__restrict__ pool, const long l
                 const int node = P.layer_off[d] + i;
                 const float2 v = bab[node];
                 const unsigned char s = bst[node];
-                const float3 o = lut[node];
-                la3dm_leaf L;
-                L.block_key = key; L.depth = d; L.index = i;
-                L.x = o.x + cx; L.y = o.y + cy; L.z = o.z + cz;                       // Block::get_loc
-                L.size = (float) ((double) P.block_size / pow(2.0, (double) d));      // Block::get_size
-                L.a = v.x; L.b = v.y;
-                if (P.method == LA3DM_GP) {
-                    // gpoctree_node.cpp:31-34, gpoctree_node.h:60
-                    L.prob = 1.0f / (1.0f + (float) exp((double) (-P.l * v.x / P.max_ivar)));
-                    L.var = 1.0f / v.y;
-                } else if (P.method == LA3DM_BGKLV) {
-                    // bgklvoctree_node.cpp:29-62
-                    const float W = (v.x + v.y < P.min_W) ? P.min_W : v.x + v.y;
-                    float pr;
-                    if (v.x > v.y) pr = (float) ((double) (v.x / (W - v.y)) + (double) (W - v.x - v.y) * 0.5 / (double) (W - v.y));
-                    else pr = (float) (0.5 * (double) (W - v.y - v.x) / (double) (W - v.x));
-                    L.prob = pr;
-                    L.var = (float) ((double) (v.x / W) * pow((double) (1 - pr), 2.0) +
-                                     (double) ((W - v.x - v.y) / W) * pow(0.5 - (double) pr, 2.0) +
-                                     (double) (v.y / W) * pow((double) pr, 2.0));
-                } else {
-                    L.prob = v.x / (v.x + v.y);                                        // bgkoctree_node.cpp:27-29
-                    L.var = (v.x * v.y) / ((v.x + v.y) * (v.x + v.y) * (v.x + v.y + 1.0f));   // bgkoctree_node.h:60
-                }
-                L.state = s & 7; L.classified = s >> 7; for (int q = 0; q < 6; ++q) L._pad[q] = 0;
+                const la3dm_leaf L = make_leaf(P, key, d, i, v, s, lut[node], cx, cy, cz);
                 out[pos] = L;
             }
             base += __popc(m);

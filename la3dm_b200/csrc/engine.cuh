@@ -112,6 +112,12 @@ struct Map {
     long long count_leaves();
     void export_leaves(la3dm_leaf *out, size_t cap, size_t *n);
     void sorted_block_order(DevBuf &order, size_t n);
+    // query / import / serialisation (query.cu)
+    void search(const float *xyz, size_t n, size_t stride_bytes, bool device_ptr, int finest_only, la3dm_leaf *out);
+    void import_blocks(const int64_t *keys, const la3dm_node *nodes, size_t n);
+    void rebuild_hash();
+    void save(const char *path);
+    void load(const char *path);
 
     unsigned char *record(size_t slot) const { return pool.as<unsigned char>() + slot * (size_t) hp.rec_bytes; }
 };

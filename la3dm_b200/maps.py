@@ -9,6 +9,7 @@ so that parity tests read like a reference node: `m = BGKOctoMap(...); m.insert_
 max_range); for leaf in m.leaves(): ...`.  All work happens in the CUDA library; this file only marshals buffers.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -144,6 +145,28 @@ class _OctoMapBase:
         if n.value:
             self._check(self._lib.la3dm_export_blocks(self._h, keys.ctypes.data, None, n.value, C.byref(n)))
         return keys, None
+
+    def search(self, xyz, finest_only=False):
+        """search(point3f) for a batch of points [n, 3] -> structured array of n records (LEAF_DTYPE); depth == -1 where
+        the block does not exist (upstream returns a default OcTreeNode there)."""
+        q = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(q), LEAF_DTYPE)
+        if len(q):
+            self._check(self._lib.la3dm_search(self._h, q.ctypes.data, len(q), 12, 1 if finest_only else 0,
+                                               out.ctypes.data))
+        return out
+
+    def import_blocks(self, keys, nodes):
+        """Inverse of blocks(): fills an empty map from (keys [B], nodes [B, nodes_per_block])."""
+        keys = np.ascontiguousarray(keys, dtype=np.int64)
+        nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        self._check(self._lib.la3dm_import_blocks(self._h, keys.ctypes.data, nodes.ctypes.data, len(keys)))
+
+    def save(self, path):
+        self._check(self._lib.la3dm_save(self._h, os.fsencode(path)))
+
+    def load(self, path):
+        self._check(self._lib.la3dm_load(self._h, os.fsencode(path)))
 
     def get_bbox(self):
         mn = np.zeros(3, np.float32)
