@@ -300,8 +300,9 @@ void Map::ensure_workspace() {
         moved |= gp_off.reserve(((size_t) caps.members + 2) * 8, stream);
         moved |= gp_store.reserve((size_t) caps.gp_store * 4, stream);
         moved |= plan_db.reserve((size_t) caps.tests * 8 * 4, stream);
-        gp_ctas = num_sms * 2;
-        moved |= gp_scratch.reserve((size_t) gp_ctas * 4 * 2 * caps.gp_n_max * 64 * 4, stream);
+        gp_ctas = num_sms * 8;
+        moved |= gp_scratch.reserve((size_t) gp_ctas * 4 * 2 * caps.gp_n_max * 32 * 4, stream);
+        moved |= gp_mv.reserve((size_t) std::min<size_t>(caps.tests, 32768) * 7 * 64 * 8, stream);
     }
     const size_t tmp = std::max(radix_sort_temp_bytes((unsigned int) n_sort),
                                 hp.method == LA3DM_GP ? scan_temp_bytes(caps.members) : (size_t) 0);
@@ -398,7 +399,8 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }
 
-    n_blocks = frontend_only ? n_blocks : (long long) h_cnt->n_blocks;
+    // blocks after the scan = blocks before + blocks k_plan / k_lv_blocks created (no overflow on this path)
+    n_blocks = frontend_only ? n_blocks : (long long) h_args->n_blocks + (long long) h_cnt->n_new_blocks;
     last_T = frontend_only ? 0 : h_cnt->n_test_blocks;
     stats.n_hits = h_cnt->n_hits;
     stats.n_train = h_cnt->n_train;

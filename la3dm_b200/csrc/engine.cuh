@@ -49,7 +49,7 @@ struct Map {
     DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
     DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
     DevBuf test_id, plan, heavy_list;
-    DevBuf gp_sizes, gp_off, gp_store, gp_scratch, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
+    DevBuf gp_sizes, gp_off, gp_store, gp_scratch, gp_mv, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
     DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists
     DevBuf lv_range, lv_info, ray_first, lv_qgrid, lv_active, lv_blk_slot, lv_blk_flags;   // BGKLVOctoMap

@@ -323,7 +323,7 @@ k_vg_long_flags(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__
 
 template <int W>
 __global__ void __launch_bounds__(kLongThreads, 1)
-k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, const float4 *__restrict__ frees_raw,
+k_vg_long(const ScanArgs *__restrict__ A, ScanCounters *c, const float4 *__restrict__ frees_raw,
           const unsigned int *__restrict__ vals, const unsigned int *__restrict__ run_start, float4 *out,
           const unsigned int *__restrict__ long_list, const float *__restrict__ lf_first,
           const unsigned char *__restrict__ lf_same, unsigned int n_sub_cap, unsigned int *mm_xy) {
@@ -332,6 +332,8 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
     __shared__ __align__(16) float stage[3][kSub];
     __shared__ __align__(16) float wstage[kLongThreads / 32][3][kMidSub];
     if (c->overflow) return;
+    // last kernel of the free-space voxel grid: the training set is complete (hits, then free centroids)
+    if (W == 1 && blockIdx.x == 0 && threadIdx.x == 0) c->n_train = c->n_hits + c->n_frees;
     const unsigned int nl = min(c->n_long_runs[W], (unsigned int) kMaxLongRuns);
     const unsigned int nm = min(c->n_mid_runs[W], (unsigned int) kMaxMidRuns);
     const float *in; int stride; unsigned int n;
@@ -386,6 +388,23 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
         // pieces: head [run_first, g0 * kSub), whole sub-chunks g0 .. g1 - 1, tail [g1 * kSub, run_last)
         unsigned int pos = run_first;
         unsigned int g = g0;
+        // The head and the tail are fetched up front, together with the first pass of flags: three dependent round
+        // trips (index, point, sum) in parallel instead of one after the other.  Threads 0..255 hold the head piece,
+        // 256..511 the tail piece.
+        const unsigned int a_len = (g0 < g1 && run_first == g0 * kSub)
+                                       ? 0u : min(((g0 < g1) ? g0 * kSub : run_last) - run_first, (unsigned int) kSub);
+        const unsigned int b_pos = g1 * kSub;
+        const unsigned int b_len = (g0 < g1 && g1 - g0 <= (unsigned int) kSubsPerPass && b_pos < run_last)
+                                       ? min(run_last - b_pos, (unsigned int) kSub) : 0u;
+        float pre[3] = {0.f, 0.f, 0.f};
+        {
+            const unsigned int tq = threadIdx.x & (kSub - 1);
+            const bool is_a = threadIdx.x < (unsigned int) kSub;
+            if (is_a ? tq < a_len : tq < b_len) {
+                const float *p = in + (size_t) vals[(is_a ? run_first : b_pos) + tq] * stride;
+                pre[0] = p[0]; pre[1] = p[1]; pre[2] = p[2];
+            }
+        }
         while (pos < run_last) {
             if (g < g1 && pos == g * kSub) {
                 const unsigned int nb = min(g1 - g, (unsigned int) kSubsPerPass);
@@ -425,7 +444,12 @@ k_vg_long(const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ c, co
                 // head, tail, or sub-chunks beyond the flag capacity: staged
                 const unsigned int end = (g < g1) ? g * kSub : run_last;
                 const unsigned int m = min(end - pos, (unsigned int) kSub);
-                if (threadIdx.x < m) {
+                if (pos == run_first && a_len == m) {                  // the prefetched head
+                    if (threadIdx.x < m) { stage[0][threadIdx.x] = pre[0]; stage[1][threadIdx.x] = pre[1]; stage[2][threadIdx.x] = pre[2]; }
+                } else if (b_len && pos == b_pos && b_len == m) {      // the prefetched tail
+                    const unsigned int tq = threadIdx.x - (unsigned int) kSub;
+                    if (threadIdx.x >= (unsigned int) kSub && tq < m) { stage[0][tq] = pre[0]; stage[1][tq] = pre[1]; stage[2][tq] = pre[2]; }
+                } else if (threadIdx.x < m) {
                     const float *p = in + (size_t) vals[pos + threadIdx.x] * stride;
                     stage[0][threadIdx.x] = p[0]; stage[1][threadIdx.x] = p[1]; stage[2][threadIdx.x] = p[2];
                 }
@@ -580,11 +604,6 @@ k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__r
     block_minmax_box(any_h, hmn, hmx, mm_xy, s_mm);
 }
 
-__global__ void k_finish_train(ScanCounters *c) {
-    if (c->overflow) return;
-    c->n_train = c->n_hits + c->n_frees;
-}
-
 inline int bits_for(unsigned int n) {   // radix-sort end bit for keys < n
     int b = 1;
     while (b < 32 && (1ull << b) < (unsigned long long) n) ++b;
@@ -660,8 +679,6 @@ void Map::enqueue_frontend_bgk() {
                                                  frees_raw.as<float4>(), caps.raw, d_mm + 6, d_mm + 12);
     launches += 2;
     enqueue_voxel_grid(1);
-    k_finish_train<<<1, 1, 0, stream>>>(d_cnt);
-    ++launches;
 }
 
 // The whole scan, stream-ordered, no host synchronisation (this is what the CUDA graph captures).

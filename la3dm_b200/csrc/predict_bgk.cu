@@ -901,10 +901,6 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     }
 }
 
-__global__ void k_scan_end(ScanCounters *c, const ScanArgs *__restrict__ A) {
-    c->n_blocks = A->n_blocks + (c->overflow ? 0u : c->n_new_blocks);
-}
-
 }  // namespace
 
 void Map::enqueue_predict() {
@@ -938,9 +934,7 @@ void Map::enqueue_predict() {
     ++launches;
 }
 
-void Map::enqueue_scan_end() {
-    k_scan_end<<<1, 1, 0, stream>>>(d_cnt, d_args);
-    ++launches;
-}
+// (the block count after the scan is derived on the host from ScanCounters::n_new_blocks: no closing kernel)
+void Map::enqueue_scan_end() {}
 
 }  // namespace la3dm_b200

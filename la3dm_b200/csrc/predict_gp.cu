@@ -147,10 +147,22 @@ k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_s
             __syncwarp();
         }
         // Backward: s = alpha_i - sum_{k > i, ascending} L_ki alpha_k needs every later alpha first: one lane
+        // (the loads of eight terms are issued together, the subtractions stay one after the other in ascending k)
         if (lane == 0) {
             for (unsigned int ii = n; ii-- > 0;) {
                 float s = alpha[ii];
-                for (unsigned int k = ii + 1; k < n; ++k) s -= L[(size_t) k * (k + 1) / 2 + ii] * alpha[k];
+                unsigned int k = ii + 1;
+                for (; k + 8 <= n; k += 8) {
+                    float l[8], a8[8];
+#pragma unroll
+                    for (unsigned int q = 0; q < 8; ++q) {
+                        l[q] = L[(size_t) (k + q) * (k + q + 1) / 2 + ii];
+                        a8[q] = alpha[k + q];
+                    }
+#pragma unroll
+                    for (unsigned int q = 0; q < 8; ++q) s -= l[q] * a8[q];
+                }
+                for (; k < n; ++k) s -= L[(size_t) k * (k + 1) / 2 + ii] * alpha[k];
                 alpha[ii] = s / L[(size_t) ii * (ii + 1) / 2 + ii];
             }
         }
@@ -174,16 +186,91 @@ struct GpWarpSmem {
     uint4 rec[kRecMax / 16];
 };
 
-// one warp per test block; a lane owns up to two leaves; for every neighbour with a trained regressor each leaf runs
-// GPRegressor::predict for its centre: ks (n kernel values), m = ks . alpha, forward substitution with L.
-// `scratch` holds ks / v per leaf: [warp][2 arrays][n_max][64 leaves]
+constexpr int kGpChunk = 32768;       // test blocks per (k_gp_mv, k_gp_apply) pair: bounds the (mean, variance) buffer
+
+// GPRegressor::predict for one (test block, neighbour, half of the leaves): a warp per unit, a lane per leaf.
+//   ks (n kernel values), m = ks . alpha, forward substitution with L, var = sf2 - v . v   (gpregressor.h:80-92)
+// Nothing here depends on the order of the neighbours, so the 7 x 2 units of a test block run in parallel; the
+// sequential part -- Occupancy::update neighbour after neighbour -- is k_gp_apply.
+// `scratch` holds ks / v per leaf: [warp][2 arrays][n_max][32 leaves]; mv: [block - t0][7][64] (mean, variance).
 __global__ void __launch_bounds__(kGpWarps * 32)
-k_gp_predict(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__ plan_db,
-             const float4 *__restrict__ pts, const unsigned long long *__restrict__ off,
-             const float *__restrict__ store,
-             const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
-             const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt, float *scratch,
-             unsigned int n_max) {
+k_gp_mv(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__ plan_db,
+        const float4 *__restrict__ pts, const unsigned long long *__restrict__ off, const float *__restrict__ store,
+        const long long *__restrict__ keys, const unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
+        const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ cnt,
+        float *scratch, unsigned int n_max, unsigned int t0, float2 *mv) {
+    __shared__ DevParams Ps;
+    load_params(Ps, Pg);
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int T = cnt->n_test_blocks;
+    if (t0 >= T) return;
+    const unsigned int t1 = min(T, t0 + (unsigned int) kGpChunk);
+    const unsigned int gw = blockIdx.x * kGpWarps + warp, n_w = gridDim.x * kGpWarps;
+    float *ks = scratch + (size_t) gw * 2 * n_max * 32;       // [n_max][32]
+    float *vv = ks + (size_t) n_max * 32;
+    const float sf2 = P.sf2, bs = P.block_size;
+    const float scale = (float) (1.73205 / (double) P.ell);    // gpregressor.h:115
+    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
+    const unsigned int units = (t1 - t0) * 14u;
+    for (unsigned int u = gw; u < units; u += n_w) {
+        const unsigned int t = t0 + u / 14u, r = u % 14u;
+        const int nb = (int) (r >> 1), s = (int) (r & 1u);
+        if (t % shard_world != shard_rank) continue;
+        const NeighbourPlan *pl = plan + t;
+        const unsigned int n = pl->count[nb];
+        if (n == 0) continue;
+        const unsigned int slot = pl->slot;
+        // this lane's leaf of the half (a fresh block has no record yet: all finest voxels)
+        int node = -1;
+        const int j = lane + 32 * s;
+        if (j < P.finest) {
+            if (pl->is_new) node = P.layer_off[P.depth - 1] + j;
+            else {
+                const unsigned char *rst = pool + (size_t) slot * (size_t) P.rec_bytes + P.st_off;
+                int d = P.depth - 1, i = j, shift = 0;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == kStPRUNED) { --d; i >>= 3; shift += 3; }
+                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != kStPRUNED)) node = P.layer_off[d] + i;
+            }
+        }
+        if (!__any_sync(0xffffffffu, node >= 0)) continue;
+        if (node >= 0) {
+            const long long key = keys[slot];
+            const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
+                        cz = axis_center(key & 0xFFFFF, bs);
+            const float3 o = lut[node];
+            // Block::get_loc, then predict()'s  scale * xs  (:84-85 with the stand-in's operand order)
+            const float qx = scale * (o.x + cx), qy = scale * (o.y + cy), qz = scale * (o.z + cz);
+            const float4 *x = pts + pl->start[nb];
+            const float *L = store + off[plan_db[(size_t) t * 8 + nb] - 1];
+            const float *alpha = L + (size_t) n * (n + 1) / 2;
+            float mu = 0.f;
+            for (unsigned int i = 0; i < n; ++i) {
+                const float4 xi = x[i];
+                const float k = matern3(xi.x, xi.y, xi.z, qx, qy, qz, sf2);
+                ks[(size_t) i * 32 + lane] = k;
+                mu += k * alpha[i];
+            }
+            float v2 = 0.f;
+            for (unsigned int i = 0; i < n; ++i) {
+                const float *ri = L + (size_t) i * (i + 1) / 2;
+                float sacc = ks[(size_t) i * 32 + lane];
+                for (unsigned int k = 0; k < i; ++k) sacc -= ri[k] * vv[(size_t) k * 32 + lane];
+                const float vi = sacc / ri[i];
+                vv[(size_t) i * 32 + lane] = vi;
+                v2 += vi * vi;
+            }
+            mv[((size_t) (t - t0) * 7 + nb) * 64 + j] = make_float2(mu, sf2 - v2);
+        }
+    }
+}
+
+// one warp per test block; a lane owns up to two leaves: Occupancy::update with the (mean, variance) of every
+// neighbour that has a trained regressor, in ExtendedBlock order (gpoctomap.cpp:305-319), then prune and write back
+__global__ void __launch_bounds__(kGpWarps * 32)
+k_gp_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ pool, const DevParams *__restrict__ Pg,
+           const ScanArgs *__restrict__ A, ScanCounters *cnt, unsigned int t0, const float2 *__restrict__ mv) {
     __shared__ GpWarpSmem sm[kGpWarps];
     __shared__ DevParams Ps;
     load_params(Ps, Pg);
@@ -192,42 +279,33 @@ k_gp_predict(const NeighbourPlan *__restrict__ plan, const unsigned int *__restr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     GpWarpSmem &S = sm[warp];
     const unsigned int T = cnt->n_test_blocks;
+    if (t0 >= T) return;
+    const unsigned int t1 = min(T, t0 + (unsigned int) kGpChunk);
     const unsigned int gw = blockIdx.x * kGpWarps + warp, n_w = gridDim.x * kGpWarps;
-    float *ks = scratch + (size_t) gw * 2 * n_max * 64;       // [n_max][64]
-    float *vv = ks + (size_t) n_max * 64;
-    const float sf2 = P.sf2, bs = P.block_size;
-    const float scale = (float) (1.73205 / (double) P.ell);    // gpregressor.h:115
-    const int shard_world = A->shard_world, shard_rank = A->shard_rank;
+    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
     float2 *rab = reinterpret_cast<float2 *>(S.rec);
     unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + P.st_off;
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
-    for (unsigned int u = gw;; u += n_w) {
-        const unsigned int t = u * (unsigned int) shard_world + (unsigned int) shard_rank;
-        if (t >= T) break;
+    for (unsigned int t = t0 + gw; t < t1; t += n_w) {
+        if (t % shard_world != shard_rank) continue;
         const NeighbourPlan pl = plan[t];
         uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
         __syncwarp();
         stage_record(S.rec, grec, pl.is_new != 0, P, lane);
-        const long long key = keys[pl.slot];
-        const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
-                    cz = axis_center(key & 0xFFFFF, bs);
         __syncwarp();
         int node[2];
         resolve_leaves(rst, P, lane, node);
-        float qx[2], qy[2], qz[2], a[2], b[2];
+        float a[2], b[2];
         unsigned char state[2];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            qx[s] = qy[s] = qz[s] = a[s] = b[s] = 0.f;
+            a[s] = b[s] = 0.f;
             state[s] = LA3DM_UNKNOWN;
             if (node[s] >= 0) {
                 const float2 v = rab[node[s]];
                 a[s] = v.x; b[s] = v.y;
                 state[s] = rst[node[s]];
-                const float3 o = lut[node[s]];
-                // Block::get_loc, then predict()'s  scale * xs  (:84-85 with the stand-in's operand order)
-                qx[s] = scale * (o.x + cx); qy[s] = scale * (o.y + cy); qz[s] = scale * (o.z + cz);
                 ++visits;
             }
         }
@@ -235,31 +313,12 @@ k_gp_predict(const NeighbourPlan *__restrict__ plan, const unsigned int *__restr
         for (int nb = 0; nb < 7; ++nb) {
             const unsigned int n = pl.count[nb];
             if (n == 0) continue;
-            const float4 *x = pts + pl.start[nb];
-            const float *L = store + off[plan_db[(size_t) t * 8 + nb] - 1];
-            const float *alpha = L + (size_t) n * (n + 1) / 2;
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (node[s] < 0) continue;
-                const int leaf = lane + 32 * s;
                 pairs += n;
-                float mu = 0.f;
-                for (unsigned int i = 0; i < n; ++i) {
-                    const float4 xi = x[i];
-                    const float k = matern3(xi.x, xi.y, xi.z, qx[s], qy[s], qz[s], sf2);
-                    ks[(size_t) i * 64 + leaf] = k;
-                    mu += k * alpha[i];
-                }
-                float v2 = 0.f;
-                for (unsigned int i = 0; i < n; ++i) {
-                    const float *ri = L + (size_t) i * (i + 1) / 2;
-                    float sacc = ks[(size_t) i * 64 + leaf];
-                    for (unsigned int k = 0; k < i; ++k) sacc -= ri[k] * vv[(size_t) k * 64 + leaf];
-                    const float vi = sacc / ri[i];
-                    vv[(size_t) i * 64 + leaf] = vi;
-                    v2 += vi * vi;
-                }
-                state[s] = gp_update(a[s], b[s], mu, sf2 - v2, P, state[s]) | 0x80;     // gpoctomap.cpp:317
+                const float2 m = mv[((size_t) (t - t0) * 7 + nb) * 64 + lane + 32 * s];
+                state[s] = gp_update(a[s], b[s], m.x, m.y, P, state[s]) | 0x80;     // gpoctomap.cpp:317
                 touched = true;
             }
         }
@@ -327,12 +386,19 @@ void Map::enqueue_gp() {
     record_event(ev_p0);
     k_gp_train<<<ctas, kGpWarps * 32, 0, stream>>>(pts_sorted.as<float4>(), db_start.as<unsigned int>(), off,
                                                    gp_store.as<float>(), d_params, d_cnt);
-    k_gp_predict<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), plan_db.as<unsigned int>(),
-                                                        pts_sorted.as<float4>(), off, gp_store.as<float>(),
-                                                        keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
-                                                        d_args, d_cnt, gp_scratch.as<float>(), caps.gp_n_max);
+    // predict: (mean, variance) of every (test block, neighbour, leaf) in parallel, then the sequential fusion per block
+    for (unsigned int t0 = 0; t0 < caps.tests; t0 += (unsigned int) kGpChunk) {
+        k_gp_mv<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), plan_db.as<unsigned int>(),
+                                                       pts_sorted.as<float4>(), off, gp_store.as<float>(),
+                                                       keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
+                                                       d_args, d_cnt, gp_scratch.as<float>(), caps.gp_n_max, t0,
+                                                       gp_mv.as<float2>());
+        k_gp_apply<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pool.as<unsigned char>(), d_params,
+                                                          d_args, d_cnt, t0, gp_mv.as<float2>());
+        launches += 2;
+    }
     record_event(ev_p1);
-    launches += 2;
+    launches += 1;
 }
 
 size_t scan_temp_bytes(unsigned int items) {
