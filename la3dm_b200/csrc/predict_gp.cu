@@ -20,6 +20,7 @@ namespace la3dm_b200 {
 namespace {
 
 constexpr int kGpWarps = 4;           // warps per CTA in both kernels
+constexpr int kGpSmemN = 64;          // k_gp_train factorises blocks of up to this many points in shared memory
 
 // expf as the reference's host libm computes it: glibc >= 2.27 (the algorithm of ARM's optimized-routines expf,
 // sysdeps/ieee754/flt-32/e_expf.c): x N / ln2 = k + r, exp(x) = 2^(k/N) 2^(r/N) ~ T[k % N] 2^(k/N int part)
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kGpWarps * 32)
 k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_start,
            const unsigned long long *__restrict__ off, float *store, const DevParams *__restrict__ Pg,
            const ScanCounters *__restrict__ c) {
+    __shared__ float sL[kGpWarps][kGpSmemN * (kGpSmemN + 1) / 2 + kGpSmemN];
     if (c->overflow) return;
     const int lane = threadIdx.x & 31;
     const unsigned int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_w = (gridDim.x * blockDim.x) >> 5;
@@ -98,7 +100,11 @@ k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_s
     for (unsigned int d = gw; d < D; d += n_w) {
         const unsigned int first = db_start[d], n = db_start[d + 1] - first;
         const float4 *x = pts + first;
-        float *L = store + off[d];                       // L[i][j] at i (i + 1) / 2 + j
+        float *Lg = store + off[d];                      // L[i][j] at i (i + 1) / 2 + j, then alpha
+        // a block of up to kGpSmemN points is factorised in shared memory (the column sweeps are chains of dependent
+        // loads: ~25 cycles each there, several hundred from L2) and copied out at the end
+        const bool staged = n <= (unsigned int) kGpSmemN;
+        float *L = staged ? sL[threadIdx.x >> 5] : Lg;
         float *alpha = L + (size_t) n * (n + 1) / 2;
         // K + noise I, lower triangle (:44-46)
         for (unsigned int i = 0; i < n; ++i) {
@@ -123,7 +129,13 @@ k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_s
                 if (i < n) {
                     ri = L + (size_t) i * (i + 1) / 2;
                     s = ri[j];
-                    for (unsigned int k = 0; k < j; ++k) s -= ri[k] * rj[k];
+                    unsigned int k = 0;
+                    for (; k + 4 <= j; k += 4) {        // loads of four terms together, subtractions in ascending k
+                        const float a0 = ri[k], a1 = ri[k + 1], a2 = ri[k + 2], a3 = ri[k + 3];
+                        const float b0 = rj[k], b1 = rj[k + 1], b2 = rj[k + 2], b3 = rj[k + 3];
+                        s -= a0 * b0; s -= a1 * b1; s -= a2 * b2; s -= a3 * b3;
+                    }
+                    for (; k < j; ++k) s -= ri[k] * rj[k];
                 }
                 if (i0 == j) {       // lane 0 holds the diagonal element
                     const float dg = sqrtf(s);
@@ -167,6 +179,11 @@ k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_s
             }
         }
         __syncwarp();
+        if (staged) {
+            const unsigned int words = n * (n + 1) / 2 + n;
+            for (unsigned int w = lane; w < words; w += 32) Lg[w] = L[w];
+            __syncwarp();
+        }
     }
 }
 
