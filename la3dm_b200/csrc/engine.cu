@@ -302,7 +302,10 @@ void Map::ensure_workspace() {
         moved |= plan_db.reserve((size_t) caps.tests * 8 * 4, stream);
         gp_ctas = num_sms * 8;
         moved |= gp_scratch.reserve((size_t) gp_ctas * 4 * 2 * caps.gp_n_max * 32 * 4, stream);
-        moved |= gp_mv.reserve((size_t) std::min<size_t>(caps.tests, 32768) * 7 * 64 * 8, stream);
+        {   // (mean, variance) of one chunk of test blocks: gp_chunk() blocks x 7 neighbours x leaves (predict_gp.cu)
+            const size_t groups = (size_t) (hp.finest + 31) / 32, chunk = std::max<size_t>(1, 65536 / groups);
+            moved |= gp_mv.reserve(std::min<size_t>(caps.tests, chunk) * 7 * groups * 32 * 8, stream);
+        }
     }
     const size_t tmp = std::max(radix_sort_temp_bytes((unsigned int) n_sort),
                                 hp.method == LA3DM_GP ? scan_temp_bytes(caps.members) : (size_t) 0);

@@ -199,23 +199,23 @@ __device__ __forceinline__ unsigned char gp_update(float &a, float &b, float m, 
     return p > P.occupied_thresh ? LA3DM_OCCUPIED : (p < P.free_thresh ? LA3DM_FREE : LA3DM_UNKNOWN);
 }
 
-struct GpWarpSmem {
-    uint4 rec[kRecMax / 16];
-};
+// test blocks per (k_gp_mv, k_gp_apply) pair: bounds the (mean, variance) buffer at 64 leaves x 32768 blocks x 7 x 8 B
+inline unsigned int gp_chunk(const DevParams &P) {
+    const unsigned int groups = (unsigned int) (P.finest + 31) / 32;
+    return std::max(1u, 65536u / groups);
+}
 
-constexpr int kGpChunk = 32768;       // test blocks per (k_gp_mv, k_gp_apply) pair: bounds the (mean, variance) buffer
-
-// GPRegressor::predict for one (test block, neighbour, half of the leaves): a warp per unit, a lane per leaf.
+// GPRegressor::predict for one (test block, neighbour, group of 32 leaves): a warp per unit, a lane per leaf.
 //   ks (n kernel values), m = ks . alpha, forward substitution with L, var = sf2 - v . v   (gpregressor.h:80-92)
-// Nothing here depends on the order of the neighbours, so the 7 x 2 units of a test block run in parallel; the
+// Nothing here depends on the order of the neighbours, so the 7 x groups units of a test block run in parallel; the
 // sequential part -- Occupancy::update neighbour after neighbour -- is k_gp_apply.
-// `scratch` holds ks / v per leaf: [warp][2 arrays][n_max][32 leaves]; mv: [block - t0][7][64] (mean, variance).
+// `scratch` holds ks / v per leaf: [warp][2 arrays][n_max][32 leaves]; mv: [block - t0][7][32 groups] (mean, variance).
 __global__ void __launch_bounds__(kGpWarps * 32)
 k_gp_mv(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__ plan_db,
         const float4 *__restrict__ pts, const unsigned long long *__restrict__ off, const float *__restrict__ store,
         const long long *__restrict__ keys, const unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
         const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ cnt,
-        float *scratch, unsigned int n_max, unsigned int t0, float2 *mv) {
+        float *scratch, unsigned int n_max, unsigned int t0, unsigned int chunk, float2 *mv) {
     __shared__ DevParams Ps;
     load_params(Ps, Pg);
     if (cnt->overflow) return;
@@ -223,23 +223,25 @@ k_gp_mv(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int T = cnt->n_test_blocks;
     if (t0 >= T) return;
-    const unsigned int t1 = min(T, t0 + (unsigned int) kGpChunk);
+    const unsigned int t1 = min(T, t0 + chunk);
     const unsigned int gw = blockIdx.x * kGpWarps + warp, n_w = gridDim.x * kGpWarps;
     float *ks = scratch + (size_t) gw * 2 * n_max * 32;       // [n_max][32]
     float *vv = ks + (size_t) n_max * 32;
     const float sf2 = P.sf2, bs = P.block_size;
     const float scale = (float) (1.73205 / (double) P.ell);    // gpregressor.h:115
     const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
-    const unsigned int units = (t1 - t0) * 14u;
+    const unsigned int groups = (unsigned int) (P.finest + 31) / 32, per_block = 7u * groups;
+    const unsigned int units = (t1 - t0) * per_block;
+    const int pruned = P.pruned_state;
     for (unsigned int u = gw; u < units; u += n_w) {
-        const unsigned int t = t0 + u / 14u, r = u % 14u;
-        const int nb = (int) (r >> 1), s = (int) (r & 1u);
+        const unsigned int t = t0 + u / per_block, r = u % per_block;
+        const int nb = (int) (r / groups), s = (int) (r % groups);
         if (t % shard_world != shard_rank) continue;
         const NeighbourPlan *pl = plan + t;
         const unsigned int n = pl->count[nb];
         if (n == 0) continue;
         const unsigned int slot = pl->slot;
-        // this lane's leaf of the half (a fresh block has no record yet: all finest voxels)
+        // this lane's leaf of the group (a fresh block has no record yet: all finest voxels)
         int node = -1;
         const int j = lane + 32 * s;
         if (j < P.finest) {
@@ -247,8 +249,8 @@ k_gp_mv(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__
             else {
                 const unsigned char *rst = pool + (size_t) slot * (size_t) P.rec_bytes + P.st_off;
                 int d = P.depth - 1, i = j, shift = 0;
-                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == kStPRUNED) { --d; i >>= 3; shift += 3; }
-                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != kStPRUNED)) node = P.layer_off[d] + i;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == pruned) { --d; i >>= 3; shift += 3; }
+                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != pruned)) node = P.layer_off[d] + i;
             }
         }
         if (!__any_sync(0xffffffffu, node >= 0)) continue;
@@ -278,30 +280,34 @@ k_gp_mv(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__
                 vv[(size_t) i * 32 + lane] = vi;
                 v2 += vi * vi;
             }
-            mv[((size_t) (t - t0) * 7 + nb) * 64 + j] = make_float2(mu, sf2 - v2);
+            mv[((size_t) (t - t0) * 7 + nb) * (groups * 32) + j] = make_float2(mu, sf2 - v2);
         }
     }
 }
 
-// one warp per test block; a lane owns up to two leaves: Occupancy::update with the (mean, variance) of every
-// neighbour that has a trained regressor, in ExtendedBlock order (gpoctomap.cpp:305-319), then prune and write back
+// one warp per test block, the record staged in (dynamic) shared memory; leaf after leaf (32 at a time, a lane each):
+// Occupancy::update with the (mean, variance) of every neighbour that has a trained regressor, in ExtendedBlock order
+// (gpoctomap.cpp:305-319); then prune and write back
 __global__ void __launch_bounds__(kGpWarps * 32)
 k_gp_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ pool, const DevParams *__restrict__ Pg,
-           const ScanArgs *__restrict__ A, ScanCounters *cnt, unsigned int t0, const float2 *__restrict__ mv) {
-    __shared__ GpWarpSmem sm[kGpWarps];
+           const ScanArgs *__restrict__ A, ScanCounters *cnt, unsigned int t0, unsigned int chunk,
+           const float2 *__restrict__ mv) {
+    extern __shared__ __align__(16) unsigned char gp_smem_raw[];
     __shared__ DevParams Ps;
     load_params(Ps, Pg);
     if (cnt->overflow) return;
     const DevParams &P = Ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    GpWarpSmem &S = sm[warp];
+    uint4 *srec = reinterpret_cast<uint4 *>(gp_smem_raw + (size_t) warp * P.rec_bytes);
     const unsigned int T = cnt->n_test_blocks;
     if (t0 >= T) return;
-    const unsigned int t1 = min(T, t0 + (unsigned int) kGpChunk);
+    const unsigned int t1 = min(T, t0 + chunk);
     const unsigned int gw = blockIdx.x * kGpWarps + warp, n_w = gridDim.x * kGpWarps;
     const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
-    float2 *rab = reinterpret_cast<float2 *>(S.rec);
-    unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + P.st_off;
+    const int groups = (P.finest + 31) / 32;
+    const int pruned = P.pruned_state;
+    float2 *rab = reinterpret_cast<float2 *>(srec);
+    unsigned char *rst = reinterpret_cast<unsigned char *>(srec) + P.st_off;
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
     for (unsigned int t = t0 + gw; t < t1; t += n_w) {
@@ -309,50 +315,42 @@ k_gp_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ p
         const NeighbourPlan pl = plan[t];
         uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
         __syncwarp();
-        stage_record(S.rec, grec, pl.is_new != 0, P, lane);
+        stage_record(srec, grec, pl.is_new != 0, P, lane);
         __syncwarp();
-        int node[2];
-        resolve_leaves(rst, P, lane, node);
-        float a[2], b[2];
-        unsigned char state[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            a[s] = b[s] = 0.f;
-            state[s] = LA3DM_UNKNOWN;
-            if (node[s] >= 0) {
-                const float2 v = rab[node[s]];
-                a[s] = v.x; b[s] = v.y;
-                state[s] = rst[node[s]];
-                ++visits;
-            }
-        }
-        bool touched = false;
-        for (int nb = 0; nb < 7; ++nb) {
-            const unsigned int n = pl.count[nb];
-            if (n == 0) continue;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (node[s] < 0) continue;
-                pairs += n;
-                const float2 m = mv[((size_t) (t - t0) * 7 + nb) * 64 + lane + 32 * s];
-                state[s] = gp_update(a[s], b[s], m.x, m.y, P, state[s]) | 0x80;     // gpoctomap.cpp:317
-                touched = true;
-            }
-        }
+        unsigned int n_total = 0;
+        for (int nb = 0; nb < 7; ++nb) n_total += pl.count[nb];
         bool any = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-            if (node[s] >= 0 && touched) {
-                rab[node[s]] = make_float2(a[s], b[s]);
-                rst[node[s]] = state[s];
-                ++updates;
-                any = true;
+        for (int s = 0; s < groups; ++s) {
+            // leaf of finest slot j (is_leaf, gpoctree.cpp: the leaf (d, i) is handled at its first finest descendant)
+            const int j = lane + 32 * s;
+            int node = -1;
+            if (j < P.finest) {
+                int d = P.depth - 1, i = j, shift = 0;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == pruned) { --d; i >>= 3; shift += 3; }
+                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != pruned)) node = P.layer_off[d] + i;
             }
+            if (node < 0) continue;
+            ++visits;
+            pairs += n_total;
+            if (n_total == 0) continue;
+            float2 v = rab[node];
+            unsigned char state = rst[node];
+            for (int nb = 0; nb < 7; ++nb) {
+                if (pl.count[nb] == 0) continue;
+                const float2 m = mv[((size_t) (t - t0) * 7 + nb) * (size_t) (groups * 32) + j];
+                state = gp_update(v.x, v.y, m.x, m.y, P, state) | 0x80;     // gpoctomap.cpp:317
+            }
+            // (a coarse leaf's node index is below every finest node's: no lane reads what another lane writes here)
+            rab[node] = v;
+            rst[node] = state;
+            ++updates;
+            any = true;
+        }
         const bool dirty = __any_sync(0xffffffffu, any) || pl.is_new;
         __syncwarp();
         if (dirty) {
             prune_record(rab, rst, P, lane);
-            for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = S.rec[w];
+            for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = srec[w];
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -385,7 +383,8 @@ __global__ void k_gp_nmax(const unsigned int *__restrict__ db_start, ScanCounter
 
 // storage offsets of the regressors and the capacity checks (runs before the map is touched)
 void Map::enqueue_gp_sizes() {
-    if (hp.depth > 3) throw StatusError{LA3DM_ERR_UNSUPPORTED, "GPOctoMap: block_depth > 3 not supported on the GPU yet"};
+    // k_gp_apply stages a block record per warp in shared memory: 5.3 KB at depth 4, 42 KB at depth 5
+    if (hp.depth > 4) throw StatusError{LA3DM_ERR_UNSUPPORTED, "GPOctoMap: block_depth > 4 not supported on the GPU yet"};
     const unsigned int cap = caps.members;     // data blocks <= memberships
     const int grid = ceil_div(cap, 256);
     unsigned long long *sizes = gp_sizes.as<unsigned long long>(), *off = gp_off.as<unsigned long long>();
@@ -404,14 +403,17 @@ void Map::enqueue_gp() {
     k_gp_train<<<ctas, kGpWarps * 32, 0, stream>>>(pts_sorted.as<float4>(), db_start.as<unsigned int>(), off,
                                                    gp_store.as<float>(), d_params, d_cnt);
     // predict: (mean, variance) of every (test block, neighbour, leaf) in parallel, then the sequential fusion per block
-    for (unsigned int t0 = 0; t0 < caps.tests; t0 += (unsigned int) kGpChunk) {
+    const unsigned int chunk = gp_chunk(hp);
+    const size_t apply_smem = (size_t) hp.rec_bytes * kGpWarps;
+    for (unsigned int t0 = 0; t0 < caps.tests; t0 += chunk) {
         k_gp_mv<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), plan_db.as<unsigned int>(),
                                                        pts_sorted.as<float4>(), off, gp_store.as<float>(),
                                                        keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
-                                                       d_args, d_cnt, gp_scratch.as<float>(), caps.gp_n_max, t0,
+                                                       d_args, d_cnt, gp_scratch.as<float>(), caps.gp_n_max, t0, chunk,
                                                        gp_mv.as<float2>());
-        k_gp_apply<<<gp_ctas, kGpWarps * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pool.as<unsigned char>(), d_params,
-                                                          d_args, d_cnt, t0, gp_mv.as<float2>());
+        k_gp_apply<<<gp_ctas, kGpWarps * 32, apply_smem, stream>>>(plan.as<NeighbourPlan>(), pool.as<unsigned char>(),
+                                                                   d_params, d_args, d_cnt, t0, chunk,
+                                                                   gp_mv.as<float2>());
         launches += 2;
     }
     record_event(ev_p1);
