@@ -295,6 +295,11 @@ void Map::ensure_workspace() {
         moved |= segs.reserve((size_t) caps.members * 2 * sizeof(float4), stream);
         moved |= seg_start.reserve(((size_t) caps.members + 2) * 4, stream);
     }
+    if (hp.method == LA3DM_GP || hp.method == LA3DM_BGKL) {
+        // per-leaf results of one chunk of test blocks: chunk x 7 neighbours x leaves x 8 B (predict_gp.cu, predict_bgkl.cu)
+        const size_t groups = (size_t) (hp.finest + 31) / 32, chunk = std::max<size_t>(1, 65536 / groups);
+        moved |= gp_mv.reserve(std::min<size_t>(caps.tests, chunk) * 7 * groups * 32 * 8, stream);
+    }
     if (hp.method == LA3DM_GP) {
         moved |= gp_sizes.reserve(((size_t) caps.members + 2) * 8, stream);
         moved |= gp_off.reserve(((size_t) caps.members + 2) * 8, stream);
@@ -302,10 +307,6 @@ void Map::ensure_workspace() {
         moved |= plan_db.reserve((size_t) caps.tests * 8 * 4, stream);
         gp_ctas = num_sms * 8;
         moved |= gp_scratch.reserve((size_t) gp_ctas * 4 * 2 * caps.gp_n_max * 32 * 4, stream);
-        {   // (mean, variance) of one chunk of test blocks: gp_chunk() blocks x 7 neighbours x leaves (predict_gp.cu)
-            const size_t groups = (size_t) (hp.finest + 31) / 32, chunk = std::max<size_t>(1, 65536 / groups);
-            moved |= gp_mv.reserve(std::min<size_t>(caps.tests, chunk) * 7 * groups * 32 * 8, stream);
-        }
     }
     const size_t tmp = std::max(radix_sort_temp_bytes((unsigned int) n_sort),
                                 hp.method == LA3DM_GP ? scan_temp_bytes(caps.members) : (size_t) 0);

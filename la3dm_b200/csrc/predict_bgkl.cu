@@ -8,6 +8,8 @@
 //   BGKLInference::predict / point_to_line_dist / covSparseLine (include/bgkloctomap/bgklinference.h:106-141, 183-197):
 //   distance from the voxel centre to the segment, divided by ell AFTER the distance, same sparse kernel;
 //   node.update only if kbar > 0.001f (:231).
+#include <algorithm>
+
 #include "block_common.cuh"
 #include "runs.cuh"
 
@@ -105,7 +107,6 @@ __device__ __forceinline__ unsigned char bgk_classify(float a, float b, const Up
 }
 
 struct SegSmem {
-    uint4 rec[kRecMax / 16];
     float4 a[kSegTile];       // p0.xyz, label
     float4 v[kSegTile];       // p1 - p0, w = |p1 - p0|^2 (fp32, summed left to right) or -1 for a degenerate segment
     float4 b[kSegTile];       // p1
@@ -133,10 +134,23 @@ __device__ __forceinline__ float seg_dist_scaled(float qx, float qy, float qz, c
     return d / ell;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
-k_predict_bgkl(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ segs,
-               const long long *__restrict__ keys, unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
-               const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A, ScanCounters *cnt) {
+// test blocks per (k_bgkl_yk, k_bgkl_apply) pair: bounds the (ybar, kbar) buffer at 7 x leaves x 8 B per block
+inline unsigned int bgkl_chunk(const DevParams &P) {
+    const unsigned int groups = (unsigned int) (P.finest + 31) / 32;
+    return std::max(1u, 65536u / groups);
+}
+
+// BGKLInference::predict for one (test block, neighbour, group of 32 leaves): a warp per unit, a lane per leaf; the
+// neighbour's segments are streamed in tiles of 32 (staged in shared memory, culled against the block's leaf box) and
+// every lane adds them to its own (ybar, kbar) in list order.  The 7 x groups units of a test block are independent --
+// the block around the sensor, which every ray crosses, is spread over 14 warps at block_depth 3 instead of one -- and
+// the sequential part, Occupancy::update neighbour after neighbour, is k_bgkl_apply.
+// yk: [block - t0][7][32 groups] (ybar, kbar)
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_bgkl_yk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ segs, const long long *__restrict__ keys,
+          const unsigned char *__restrict__ pool, const float3 *__restrict__ lut, const DevParams *__restrict__ Pg,
+          const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ cnt, unsigned int t0, unsigned int chunk,
+          float2 *yk) {
     __shared__ SegSmem sm[kWarpsPerCta];
     __shared__ DevParams Ps;
     load_params(Ps, Pg);
@@ -145,107 +159,153 @@ k_predict_bgkl(const NeighbourPlan *__restrict__ plan, const float4 *__restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SegSmem &S = sm[warp];
     const unsigned int T = cnt->n_test_blocks;
-    const unsigned int warps_total = gridDim.x * kWarpsPerCta;
+    if (t0 >= T) return;
+    const unsigned int t1 = min(T, t0 + chunk);
+    const unsigned int gw = blockIdx.x * kWarpsPerCta + warp, n_w = gridDim.x * kWarpsPerCta;
     const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
-    const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
-    const int shard_world = A->shard_world, shard_rank = A->shard_rank;
-    float2 *rab = reinterpret_cast<float2 *>(S.rec);
-    unsigned char *rst = reinterpret_cast<unsigned char *>(S.rec) + P.st_off;
+    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
+    const unsigned int groups = (unsigned int) (P.finest + 31) / 32, per_block = 7u * groups;
+    const unsigned int units = (t1 - t0) * per_block;
+    const int pruned = P.pruned_state;
     const float reach = 0.5f * (bs - P.resolution) * 1.001f;       // leaf centres lie within this of the block centre
     const float cull2 = ell * ell * (1.0f + 1e-3f);
-    unsigned long long visits = 0, updates = 0, pairs = 0;
-
-    // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over its warps
-    for (unsigned int u = blockIdx.x * kWarpsPerCta + warp;; u += warps_total) {
-        const unsigned int t = u * (unsigned int) shard_world + (unsigned int) shard_rank;
-        if (t >= T) break;
-        const NeighbourPlan pl = plan[t];
-        uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
-        __syncwarp();
-        stage_record(S.rec, grec, pl.is_new != 0, P, lane);
-        const long long key = keys[pl.slot];
+    for (unsigned int u = gw; u < units; u += n_w) {
+        const unsigned int t = t0 + u / per_block, r = u % per_block;
+        const int nb = (int) (r / groups), s = (int) (r % groups);
+        if (t % shard_world != shard_rank) continue;
+        const NeighbourPlan *pl = plan + t;
+        const unsigned int n = pl->count[nb];
+        if (n == 0) continue;
+        const unsigned int slot = pl->slot;
+        // this lane's leaf of the group (a fresh block has no record yet: all finest voxels)
+        int node = -1;
+        const int j = lane + 32 * s;
+        if (j < P.finest) {
+            if (pl->is_new) node = P.layer_off[P.depth - 1] + j;
+            else {
+                const unsigned char *rst = pool + (size_t) slot * (size_t) P.rec_bytes + P.st_off;
+                int d = P.depth - 1, i = j, shift = 0;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == pruned) { --d; i >>= 3; shift += 3; }
+                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != pruned)) node = P.layer_off[d] + i;
+            }
+        }
+        if (!__any_sync(0xffffffffu, node >= 0)) continue;
+        const long long key = keys[slot];
         const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
                     cz = axis_center(key & 0xFFFFF, bs);
-        __syncwarp();
-        int node[2];
-        resolve_leaves(rst, P, lane, node);
-        float qx[2], qy[2], qz[2], a[2], b[2];
-        unsigned char touched[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            qx[s] = qy[s] = qz[s] = a[s] = b[s] = 0.f;
-            touched[s] = 0;
-            if (node[s] >= 0) {
-                const float2 v = rab[node[s]];
-                a[s] = v.x; b[s] = v.y;
-                const float3 o = lut[node[s]];
-                qx[s] = o.x + cx; qy[s] = o.y + cy; qz[s] = o.z + cz;       // Block::get_loc
-                ++visits;
-            }
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (node >= 0) {
+            const float3 o = lut[node];
+            qx = o.x + cx; qy = o.y + cy; qz = o.z + cz;           // Block::get_loc
         }
-        const bool have1 = __any_sync(0xffffffffu, node[1] >= 0);
-        for (int nb = 0; nb < 7; ++nb) {
-            const unsigned int n = pl.count[nb];
-            if (n == 0) continue;
-            const float4 *src = segs + 2 * (size_t) pl.start[nb];
-            pairs += (unsigned long long) n * ((node[0] >= 0) + (node[1] >= 0));
-            float yb[2] = {0.f, 0.f}, kb[2] = {0.f, 0.f};
-            for (unsigned int base = 0; base < n; base += kSegTile) {
-                const unsigned int m = min((unsigned int) kSegTile, n - base);
-                bool keep = false;
-                float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sv = sa, sb = sa;
-                if ((unsigned int) lane < m) {
-                    sa = src[2 * (size_t) (base + lane)];
-                    sb = src[2 * (size_t) (base + lane) + 1];
-                    sv = make_float4(sb.x - sa.x, sb.y - sa.y, sb.z - sa.z, 0.f);
-                    const float c2 = sv.x * sv.x + sv.y * sv.y + sv.z * sv.z;
-                    const float len = (float) sqrt((double) c2);
-                    sv.w = len < 0.0001f ? -1.0f : c2;                     // EPSILON (bgklinference.h:14)
-                    // cull: distance between the segment's bounding box and the box of the leaf centres
-                    const float gx = fmaxf(fmaxf(fminf(sa.x, sb.x) - (cx + reach), (cx - reach) - fmaxf(sa.x, sb.x)), 0.f);
-                    const float gy = fmaxf(fmaxf(fminf(sa.y, sb.y) - (cy + reach), (cy - reach) - fmaxf(sa.y, sb.y)), 0.f);
-                    const float gz = fmaxf(fmaxf(fminf(sa.z, sb.z) - (cz + reach), (cz - reach) - fmaxf(sa.z, sb.z)), 0.f);
-                    keep = gx * gx + gy * gy + gz * gz < cull2;
-                }
-                unsigned int todo = __ballot_sync(0xffffffffu, keep);
-                if (!todo) continue;
-                __syncwarp();
-                S.a[lane] = sa;
-                S.v[lane] = sv;
-                S.b[lane] = sb;
-                __syncwarp();
-                while (todo) {
-                    const int q = __ffs(todo) - 1;
-                    todo &= todo - 1;
+        const float4 *src = segs + 2 * (size_t) pl->start[nb];
+        float yb = 0.f, kb = 0.f;
+        for (unsigned int base = 0; base < n; base += kSegTile) {
+            const unsigned int m = min((unsigned int) kSegTile, n - base);
+            bool keep = false;
+            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sv = sa, sb = sa;
+            if ((unsigned int) lane < m) {
+                sa = src[2 * (size_t) (base + lane)];
+                sb = src[2 * (size_t) (base + lane) + 1];
+                sv = make_float4(sb.x - sa.x, sb.y - sa.y, sb.z - sa.z, 0.f);
+                const float c2 = sv.x * sv.x + sv.y * sv.y + sv.z * sv.z;
+                const float len = (float) sqrt((double) c2);
+                sv.w = len < 0.0001f ? -1.0f : c2;                     // EPSILON (bgklinference.h:14)
+                // cull: distance between the segment's bounding box and the box of the block's leaf centres
+                const float gx = fmaxf(fmaxf(fminf(sa.x, sb.x) - (cx + reach), (cx - reach) - fmaxf(sa.x, sb.x)), 0.f);
+                const float gy = fmaxf(fmaxf(fminf(sa.y, sb.y) - (cy + reach), (cy - reach) - fmaxf(sa.y, sb.y)), 0.f);
+                const float gz = fmaxf(fmaxf(fminf(sa.z, sb.z) - (cz + reach), (cz - reach) - fmaxf(sa.z, sb.z)), 0.f);
+                keep = gx * gx + gy * gy + gz * gz < cull2;
+            }
+            unsigned int todo = __ballot_sync(0xffffffffu, keep);
+            if (!todo) continue;
+            __syncwarp();
+            S.a[lane] = sa;
+            S.v[lane] = sv;
+            S.b[lane] = sb;
+            __syncwarp();
+            while (todo) {
+                const int q = __ffs(todo) - 1;
+                todo &= todo - 1;
+                if (node >= 0) {
                     const float4 za = S.a[q], zv = S.v[q], zb = S.b[q];
-                    if (node[0] >= 0) {
-                        const float d = seg_dist_scaled(qx[0], qy[0], qz[0], za, zv, zb, ell);
-                        if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb[0] += k * za.w; kb[0] += k; }
-                    }
-                    if (have1 && node[1] >= 0) {
-                        const float d = seg_dist_scaled(qx[1], qy[1], qz[1], za, zv, zb, ell);
-                        if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb[1] += k * za.w; kb[1] += k; }
-                    }
+                    const float d = seg_dist_scaled(qx, qy, qz, za, zv, zb, ell);
+                    if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb += k * za.w; kb += k; }
                 }
             }
-#pragma unroll
-            for (int s = 0; s < 2; ++s)       // Occupancy::update's accumulation, guarded by kbar > 0.001f (:231)
-                if (node[s] >= 0 && kb[s] > 0.001f) { a[s] += yb[s]; b[s] += kb[s] - yb[s]; touched[s] = 1; }
         }
+        if (node >= 0) yk[((size_t) (t - t0) * 7 + nb) * (size_t) (groups * 32) + j] = make_float2(yb, kb);
+    }
+}
+
+// one warp per test block; the record staged in (dynamic) shared memory when it fits (block_depth <= 4), updated in
+// place in global memory otherwise; leaf after leaf (32 at a time, a lane each): Occupancy::update's accumulation with
+// the (ybar, kbar) of every neighbour in ExtendedBlock order, guarded by kbar > 0.001f (bgkloctomap.cpp:231),
+// classification once per touched leaf; then prune and write back
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_bgkl_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ pool, const DevParams *__restrict__ Pg,
+             const ScanArgs *__restrict__ A, ScanCounters *cnt, unsigned int t0, unsigned int chunk,
+             const float2 *__restrict__ yk, int staged) {
+    extern __shared__ __align__(16) unsigned char bgkl_smem_raw[];
+    __shared__ DevParams Ps;
+    load_params(Ps, Pg);
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int T = cnt->n_test_blocks;
+    if (t0 >= T) return;
+    const unsigned int t1 = min(T, t0 + chunk);
+    const unsigned int gw = blockIdx.x * kWarpsPerCta + warp, n_w = gridDim.x * kWarpsPerCta;
+    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
+    const UpdateParams U{P.var_thresh, P.occupied_thresh, P.free_thresh};
+    const int groups = (P.finest + 31) / 32;
+    const int pruned = P.pruned_state;
+    unsigned long long visits = 0, updates = 0, pairs = 0;
+
+    for (unsigned int t = t0 + gw; t < t1; t += n_w) {
+        if (t % shard_world != shard_rank) continue;
+        const NeighbourPlan pl = plan[t];
+        uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
+        uint4 *wrec = staged ? reinterpret_cast<uint4 *>(bgkl_smem_raw + (size_t) warp * P.rec_bytes) : grec;
+        __syncwarp();
+        if (staged || pl.is_new) stage_record(wrec, grec, pl.is_new != 0, P, lane);
+        __syncwarp();
+        float2 *rab = reinterpret_cast<float2 *>(wrec);
+        unsigned char *rst = reinterpret_cast<unsigned char *>(wrec) + P.st_off;
+        unsigned int n_total = 0;
+        for (int nb = 0; nb < 7; ++nb) n_total += pl.count[nb];
         bool any = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-            if (node[s] >= 0 && touched[s]) {
-                rab[node[s]] = make_float2(a[s], b[s]);
-                rst[node[s]] = bgk_classify(a[s], b[s], U) | 0x80;
+        for (int s = 0; s < groups; ++s) {
+            const int j = lane + 32 * s;
+            int node = -1;
+            if (j < P.finest) {
+                int d = P.depth - 1, i = j, shift = 0;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == pruned) { --d; i >>= 3; shift += 3; }
+                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != pruned)) node = P.layer_off[d] + i;
+            }
+            if (node < 0) continue;
+            ++visits;
+            pairs += n_total;
+            if (n_total == 0) continue;
+            float2 v = rab[node];
+            bool touched = false;
+            for (int nb = 0; nb < 7; ++nb) {
+                if (pl.count[nb] == 0) continue;
+                const float2 m = yk[((size_t) (t - t0) * 7 + nb) * (size_t) (groups * 32) + j];
+                if (m.y > 0.001f) { v.x += m.x; v.y += m.y - m.x; touched = true; }
+            }
+            if (touched) {
+                rab[node] = v;
+                rst[node] = bgk_classify(v.x, v.y, U) | 0x80;
                 ++updates;
                 any = true;
             }
+        }
         const bool dirty = __any_sync(0xffffffffu, any) || pl.is_new;
         __syncwarp();
         if (dirty) {
             prune_record(rab, rst, P, lane);
-            for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = S.rec[w];
+            if (staged) for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = wrec[w];
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -276,14 +336,21 @@ void Map::enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int
 }
 
 void Map::enqueue_predict_bgkl() {
-    if (hp.depth > 3) throw StatusError{LA3DM_ERR_UNSUPPORTED, "BGKLOctoMap: block_depth > 3 not supported on the GPU yet"};
-    const int ctas = num_sms * 3;
+    const int ctas = num_sms * 4;
+    const unsigned int chunk = bgkl_chunk(hp);
+    const size_t rec_smem = (size_t) hp.rec_bytes * kWarpsPerCta;
+    const int staged = rec_smem <= 40 * 1024 ? 1 : 0;          // block_depth <= 4 (5.3 KB per record)
     record_event(ev_p0);
-    k_predict_bgkl<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), segs.as<float4>(),
-                                                           keys.as<long long>(), pool.as<unsigned char>(), d_lut,
-                                                           d_params, d_args, d_cnt);
+    for (unsigned int t0 = 0; t0 < caps.tests; t0 += chunk) {
+        k_bgkl_yk<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), segs.as<float4>(),
+                                                          keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
+                                                          d_args, d_cnt, t0, chunk, gp_mv.as<float2>());
+        k_bgkl_apply<<<ctas, kWarpsPerCta * 32, staged ? rec_smem : 0, stream>>>(
+            plan.as<NeighbourPlan>(), pool.as<unsigned char>(), d_params, d_args, d_cnt, t0, chunk, gp_mv.as<float2>(),
+            staged);
+        launches += 2;
+    }
     record_event(ev_p1);
-    ++launches;
 }
 
 }  // namespace la3dm_b200

@@ -61,3 +61,21 @@ def test_bgkl_other_parameters_no_range_limit(scans):
         for mm in (m, o):
             mm.insert_pointcloud(pts[s][:2000], org[s], RES, 0.25, -1.0)
         compare_leaves(m.leaves(), oracle_leaves_as_struct(o.leaves()), what="bgkl params scan %d" % s)
+
+
+@pytest.mark.parametrize("depth", [4, 5])
+def test_bgkl_deeper_blocks(scans, depth):
+    """config/methods/bgkloctomap_large_map.yaml uses block_depth 5 (4096 finest voxels per block): 128 leaf groups per
+    (test block, neighbour) in k_bgkl_yk; k_bgkl_apply works on the 42 KB record in place (depth 4: staged)."""
+    from oracle.port import PortMap
+    p = dict(BGKL)
+    p.update(block_depth=depth)
+    pts, org = scans["sim_structured"]
+    m, o = new_map(block_depth=depth), PortMap("bgkl", p)
+    for s in range(2):
+        m.insert_pointcloud(pts[s], org[s], RES, FREE_RES["bgkl"], MAX_RANGE)
+        o.insert_pointcloud(pts[s], org[s], RES, FREE_RES["bgkl"], MAX_RANGE)
+        compare_leaves(m.leaves(), oracle_leaves_as_struct(o.leaves()), what="bgkl depth %d scan %d" % (depth, s))
+        so, sg = o.last_stats(), m.last_stats()
+        for k in ("n_train", "n_test_blocks", "voxel_visits"):
+            assert so[k] == sg[k], (s, k, so[k], sg[k])
