@@ -105,3 +105,23 @@ def test_lv_half_resolution_and_pruning():
             m.insert_pointcloud(pts[::3], org, p["resolution"], FREE_RES["bgklv"], MAX_RANGE)
             r.insert_pointcloud(pts[::3], org, p["resolution"], FREE_RES["bgklv"], MAX_RANGE)
             lv_compare(m.leaves(), oracle_leaves_as_struct(r.leaves()), "lv %r scan %d" % (kw, s))
+
+
+@needs_ref
+def test_lv_large_map_configuration():
+    """config/methods/bgklvoctomap_large_map.yaml: resolution 0.2, block_depth 6 (32768 finest voxels per 6.4 m block),
+    ell 0.6, original_size, min_W 0.01, var_thresh 0.001."""
+    kw = dict(resolution=0.2, block_depth=6, sf2=0.1, ell=0.6, original_size=True, min_W=0.01, var_thresh=0.001)
+    p = dict(BGKLV)
+    p.update(kw)
+    pts, org = long_term_scan()
+    m, r = new_map(**kw), ref.RefMap("bgklv", p)
+    for s in range(2):
+        m.insert_pointcloud(pts, org, 0.5, 0.1, 30.0)          # ds_resolution 0.5 (clamped to 0.2 upstream), max_range 30
+        r.insert_pointcloud(pts, org, 0.5, 0.1, 30.0)
+        got, want = m.leaves(), oracle_leaves_as_struct(r.leaves())
+        assert len(got) == len(want)
+        for k in ("block_key", "depth", "index", "x", "y", "z", "size"):
+            assert np.array_equal(got[k], want[k]), k
+        err = np.abs(got["prob"].astype(np.float64) - want["prob"].astype(np.float64))
+        assert (err <= 1e-4 * np.abs(want["prob"]) + 1e-6).all(), float(err.max())
