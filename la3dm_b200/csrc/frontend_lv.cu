@@ -36,22 +36,27 @@ struct LvRay {
     unsigned int flags;     // bit 0: the hit is a training point, bit 1: the ray is kept
 };
 
-// one thread per hit: the whole of the per-hit body of get_training_data except the emission
-__global__ void __launch_bounds__(kHitTile)
+// One WARP per hit: the whole of the per-hit body of get_training_data except the emission.  The pass over all other
+// hits (:341-386) is O(hits^2); its candidate test and the projection onto the ray only depend on the UNshortened ray,
+// so the 32 lanes evaluate 32 hits at a time and only the hits that would shorten the ray (within `influence` of it)
+// are then applied one after the other in hit order -- the same sequence of updates of `l` as upstream's loop.
+// CTAs of 8 warps = 8 hits each, so that even a 2 000-hit scan covers every SM; the per-tile sums k_lv_fill expects
+// come from k_lv_tile_sums.
+constexpr int kRayThreads = 256;
+
+__global__ void __launch_bounds__(kRayThreads)
 k_lv_rays(const float4 *__restrict__ hits, const double *__restrict__ range, const ScanCounters *__restrict__ c,
-          const ScanArgs *__restrict__ A, const DevParams *__restrict__ P, LvRay *out,
-          unsigned long long *tile_sums) {
-    __shared__ unsigned long long s_sum;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
+          const ScanArgs *__restrict__ A, const DevParams *__restrict__ P, LvRay *out) {
     const unsigned int H = c->overflow ? 0u : c->n_ds_hits;
-    const unsigned int i = blockIdx.x * kHitTile + threadIdx.x;
-    unsigned long long acc = 0;
-    if (i < H) {
-        const float ox = A->ox, oy = A->oy, oz = A->oz;
-        const float max_range = A->max_range;
-        const double offset = (double) P->ell * pow(2.0, 0.5);       // :314
-        const double influence = (double) P->ell;                    // :315
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kPerWarp = 1;
+    const float ox = A->ox, oy = A->oy, oz = A->oz;
+    const float max_range = A->max_range;
+    const double offset = (double) P->ell * pow(2.0, 0.5);       // :314
+    const double influence = (double) P->ell;                    // :315
+    for (int hh = 0; hh < kPerWarp; ++hh) {
+        const unsigned int i = blockIdx.x * (kRayThreads / 32) + warp * kPerWarp + hh;
+        if (i >= H) break;                                           // warp-uniform
         const float4 p = hits[i];
         double l = range[i];                                         // :318
         const float nx = (float) ((double) (p.x - ox) / l), ny = (float) ((double) (p.y - oy) / l),
@@ -69,7 +74,7 @@ k_lv_rays(const float4 *__restrict__ hits, const double *__restrict__ range, con
                 l = (double) max_range - offset;                     // :333
             }
         }
-        float npx = p.x, npy = p.y, npz = p.z;                       // nearest_point (only z is used)
+        float npz = p.z;                                             // nearest_point (only z is used)
         // free_endpt (:338): float + float * double -> double, narrowed by the point3f constructor
         const float ex0 = (float) ((double) ox + (double) nx * l), ey0 = (float) ((double) oy + (double) ny * l),
                     ez0 = (float) ((double) oz + (double) nz * l);
@@ -78,26 +83,41 @@ k_lv_rays(const float4 *__restrict__ hits, const double *__restrict__ range, con
         const double lv_norm = sqrt((double) (lvx * lvx + lvy * lvy + lvz * lvz));
         const double lv_norm2 = pow(lv_norm, 2);
         const bool high = (double) p.z > (offset + (double) oz);      // first half of the floor test (:351)
-        for (unsigned int j = 0; j < H; ++j) {
-            const float4 q = hits[j];
-            const double rj = range[j];
-            if (max_range > 0 && rj > (double) max_range) continue;   // :345-348
-            if (high && (double) q.z < (double) oz + influence) continue;   // :351-353
-            const double dist1 = norm_diff(ex0, ey0, ez0, q.x, q.y, q.z);   // :355
-            if (!(dist1 < influence || (dist1 < l0 && rj < l0))) continue;  // :359-365 (dist2 == range of q)
-            // shorten the ray against this nearby point (:372-386)
-            const float vx = q.x - ox, vy = q.y - oy, vz = q.z - oz;
-            const double b = (double) (vx * lvx + vy * lvy + vz * lvz);
-            if (b > pow(l, 2)) continue;
-            const float s = (float) (b / lv_norm2);                   // operator*(float)
-            const float qx = ox + lvx * s, qy = oy + lvy * s, qz = oz + lvz * s;
-            const double dist = norm_diff(q.x, q.y, q.z, qx, qy, qz);
-            if (dist < influence) {
-                npx = q.x; npy = q.y; npz = q.z;
-                l = b / lv_norm;
+        for (unsigned int j0 = 0; j0 < H; j0 += 32) {
+            const unsigned int j = j0 + (unsigned int) lane;
+            bool shortens = false;
+            double b = 0.0;
+            float qz_hit = 0.f;
+            if (j < H) {
+                const float4 q = hits[j];
+                const double rj = range[j];
+                bool cand = !(max_range > 0 && rj > (double) max_range);          // :345-348
+                cand = cand && !(high && (double) q.z < (double) oz + influence);   // :351-353
+                if (cand) {
+                    const double dist1 = norm_diff(ex0, ey0, ez0, q.x, q.y, q.z);   // :355
+                    cand = dist1 < influence || (dist1 < l0 && rj < l0);            // :359-365 (dist2 == range of q)
+                }
+                if (cand) {
+                    // projection of the hit onto the ray (:372-384); whether it is applied depends on the current l
+                    const float vx = q.x - ox, vy = q.y - oy, vz = q.z - oz;
+                    b = (double) (vx * lvx + vy * lvy + vz * lvz);
+                    const float s = (float) (b / lv_norm2);                   // operator*(float)
+                    const float qx = ox + lvx * s, qy = oy + lvy * s, qz = oz + lvz * s;
+                    shortens = norm_diff(q.x, q.y, q.z, qx, qy, qz) < influence;
+                    qz_hit = q.z;
+                }
+            }
+            unsigned int todo = __ballot_sync(0xffffffffu, shortens);
+            while (todo) {                                           // in hit order, like the loop upstream
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const double bj = __shfl_sync(0xffffffffu, b, src);
+                const float zj = __shfl_sync(0xffffffffu, qz_hit, src);
+                if (bj > pow(l, 2)) continue;                        // :376
+                npz = zj;
+                l = bj / lv_norm;                                    // :385
             }
         }
-        (void) npx; (void) npy;
         const bool drop = l < (double) max_range / 5.0 && l / (offset - (double) npz) > 0;   // :389-391
         if (!drop) {
             r.flags |= 2u;
@@ -122,9 +142,23 @@ k_lv_rays(const float4 *__restrict__ hits, const double *__restrict__ range, con
         } else {
             r.fo[0] = r.fo[1] = r.fo[2] = r.fe[0] = r.fe[1] = r.fe[2] = 0.f;
         }
-        out[i] = r;
-        const unsigned int entries = (r.flags & 1u) + ((r.flags & 2u) ? 1u + r.n_samples : 0u);
-        acc = ((unsigned long long) ((r.flags >> 1) & 1u) << 32) | (unsigned long long) entries;
+        if (lane == 0) out[i] = r;
+    }
+}
+
+// tile_sums[tile] = (rays kept << 32) | training entries of the tile's kHitTile hits
+__global__ void __launch_bounds__(kHitTile)
+k_lv_tile_sums(const LvRay *__restrict__ info, const ScanCounters *__restrict__ c, unsigned long long *tile_sums) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const unsigned int H = c->overflow ? 0u : c->n_ds_hits;
+    const unsigned int i = blockIdx.x * kHitTile + threadIdx.x;
+    unsigned long long acc = 0;
+    if (i < H) {
+        const unsigned int flags = info[i].flags, ns = info[i].n_samples;
+        const unsigned int entries = (flags & 1u) + ((flags & 2u) ? 1u + ns : 0u);
+        acc = ((unsigned long long) ((flags >> 1) & 1u) << 32) | (unsigned long long) entries;
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&s_sum, acc);
@@ -241,8 +275,10 @@ void Map::enqueue_frontend_lv() {
     k_lv_ranges<<<grid, 256, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, lv_range.as<double>());
     const int n_tiles = ceil_div(caps.points, kHitTile);
     unsigned long long *tile_sums = tiles.as<unsigned long long>();
-    k_lv_rays<<<n_tiles, kHitTile, 0, stream>>>(hits_ds.as<float4>(), lv_range.as<double>(), d_cnt, d_args, d_params,
-                                                lv_info.as<LvRay>(), tile_sums);
+    k_lv_rays<<<ceil_div(caps.points, kRayThreads / 32), kRayThreads, 0, stream>>>(
+        hits_ds.as<float4>(), lv_range.as<double>(), d_cnt, d_args, d_params, lv_info.as<LvRay>());
+    k_lv_tile_sums<<<n_tiles, kHitTile, 0, stream>>>(lv_info.as<LvRay>(), d_cnt, tile_sums);
+    ++launches;
     k_lv_fill<<<n_tiles, kHitTile, 0, stream>>>(hits_ds.as<float4>(), d_cnt, d_args, lv_info.as<LvRay>(), tile_sums,
                                                 (unsigned int) n_tiles, xy.as<float4>(), ray_of.as<int>(),
                                                 rays.as<float4>(), ray_first.as<unsigned int>(), caps.raw, d_mm + 12);
