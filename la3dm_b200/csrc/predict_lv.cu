@@ -351,15 +351,42 @@ k_lv_predict(const uint2 *__restrict__ active, const GridDesc *__restrict__ g, c
         const VoxelQuery v = voxel_query(b.key, node, lut, P, q);
         float yb = 0.f, kb = 0.f;
         unsigned int cnt = 0;
-        for (int cx = v.c0[0]; cx <= v.c1[0]; ++cx)
-            for (int cy = v.c0[1]; cy <= v.c1[1]; ++cy)
-                for (int cz = v.c0[2]; cz <= v.c1[2]; ++cz) {
-                    const unsigned int cid = ((unsigned int) cx * (unsigned int) q.n[1] + (unsigned int) cy) *
-                                                 (unsigned int) q.n[2] + (unsigned int) cz;
-                    const unsigned int r = cell_run[cid];
-                    if (!r) continue;
-                    const unsigned int i1 = run_first[r];
-                    for (unsigned int i = run_first[r - 1] + lane; i < i1; i += 32) {
+        // The query box covers 3 x 3 x 3 cells of edge ell with a handful of entries each: a lane looks up one cell,
+        // a warp scan concatenates the cells' entry ranges, and the warp then walks the concatenation 32 entries at a
+        // time (striding over one cell at a time would leave most lanes idle).
+        const int ncy = v.c1[1] - v.c0[1] + 1, ncz = v.c1[2] - v.c0[2] + 1;
+        const int ncell = (v.c1[0] - v.c0[0] + 1) * ncy * ncz;
+        for (int cbase = 0; cbase < ncell; cbase += 32) {
+            unsigned int c_start = 0, c_cnt = 0;
+            const int ci = cbase + lane;
+            if (ci < ncell) {
+                const int cx = v.c0[0] + ci / (ncy * ncz), cy = v.c0[1] + (ci / ncz) % ncy, cz = v.c0[2] + ci % ncz;
+                const unsigned int cid = ((unsigned int) cx * (unsigned int) q.n[1] + (unsigned int) cy) *
+                                             (unsigned int) q.n[2] + (unsigned int) cz;
+                const unsigned int r = cell_run[cid];
+                if (r) { c_start = run_first[r - 1]; c_cnt = run_first[r] - c_start; }
+            }
+            unsigned int c_inc = c_cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int up = __shfl_up_sync(0xffffffffu, c_inc, d);
+                if (lane >= d) c_inc += up;
+            }
+            const unsigned int n_ent = __shfl_sync(0xffffffffu, c_inc, 31);
+            for (unsigned int e0 = 0; e0 < n_ent; e0 += 32) {
+                const unsigned int ei = e0 + (unsigned int) lane;
+                int own = 0;                                   // first cell whose inclusive count exceeds ei
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const unsigned int below = __shfl_sync(0xffffffffu, c_inc, own + step - 1);
+                    if (below <= ei) own += step;
+                }
+                own = min(own, 31);
+                const unsigned int o_inc = __shfl_sync(0xffffffffu, c_inc, own), o_cnt = __shfl_sync(0xffffffffu, c_cnt, own),
+                                   o_start = __shfl_sync(0xffffffffu, c_start, own);
+                {
+                    if (ei < n_ent) {
+                        const unsigned int i = o_start + (ei - (o_inc - o_cnt));
                         const unsigned int e = vals[i];
                         const float4 pt = xy[e];
                         if (!in_box(pt, v.lo, v.hi)) continue;
@@ -381,6 +408,8 @@ k_lv_predict(const uint2 *__restrict__ active, const GridDesc *__restrict__ g, c
                         ++cnt;
                     }
                 }
+            }
+        }
         for (int o = 16; o > 0; o >>= 1) {
             yb += __shfl_xor_sync(0xffffffffu, yb, o);
             kb += __shfl_xor_sync(0xffffffffu, kb, o);
