@@ -172,7 +172,7 @@ struct ScanCounters {
     unsigned int n_long_runs[2]; // voxel-grid runs handed to the long-run kernel, one CTA each
     unsigned int n_mid_runs[2];  // ... one warp each
     unsigned int grid_irregular;
-    unsigned int n_blocks;       // blocks in the map after the scan
+    unsigned int reserved_;      // (was: blocks after the scan -- now derived on the host from n_new_blocks)
     unsigned int vg_cells_needed;
     unsigned int gp_n_max;       // GP: largest data block of the scan
     unsigned int lv_active;      // BGKLV: active voxels of the scan

@@ -106,7 +106,6 @@ struct Map {
     void enqueue_predict();
     void enqueue_gp();
     void enqueue_gp_sizes();
-    void enqueue_scan_end();
     // export
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();

@@ -691,13 +691,11 @@ void Map::enqueue_scan(bool frontend_only) {
     else enqueue_frontend_bgk();
     if (!frontend_only && hp.method == LA3DM_BGKLV) {
         enqueue_lv();
-        enqueue_scan_end();
     } else if (!frontend_only) {
         enqueue_binning();
         if (hp.method == LA3DM_GP) enqueue_gp();
         else if (hp.method == LA3DM_BGKL) enqueue_predict_bgkl();
         else enqueue_predict();
-        enqueue_scan_end();
     }
 }
 

@@ -934,7 +934,5 @@ void Map::enqueue_predict() {
     ++launches;
 }
 
-// (the block count after the scan is derived on the host from ScanCounters::n_new_blocks: no closing kernel)
-void Map::enqueue_scan_end() {}
 
 }  // namespace la3dm_b200
