@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Per-method timing on the reference's shipped sequences (BASELINE.json configs[1..3]): la3dm_b200 through the C ABI on
+"""TEST INFRASTRUCTURE (times the checker under oracle/ next to the product; lives under tests/ for that reason).
+
+Per-method timing on the reference's shipped sequences (BASELINE.json configs[1..3]): la3dm_b200 through the C ABI on
 cuda:0 next to the reference's own sources (oracle/_ref, fast flavour, all host threads) on the same scans.
 
 Not the headline benchmark (bench.py is); prints one JSON line per method for README / profiles.  Run on a GPU box:
-    python tools/bench_methods.py > gpurun_out/methods.jsonl
+    python tests/perf/bench_methods.py > gpurun_out/methods.jsonl
 """
 import json
 import os
@@ -12,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import la3dm_b200                      # noqa: E402

@@ -1,3 +1,4 @@
+"""TEST INFRASTRUCTURE: the non-headline methods on the synthetic headline-size scans (python tests/perf/big_methods.py bgkl,gp 65536)."""
 import sys, time, json, numpy as np
 sys.path.insert(0, "/root/repo")
 import la3dm_b200
