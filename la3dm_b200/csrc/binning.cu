@@ -365,7 +365,7 @@ __global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c
         tot += count;
     }
     // heavy blocks of this rank's shard (test block t belongs to rank t % world), predicted first
-    if (heavy_list && tot > kHeavyTot && t % (unsigned int) A->shard_world == (unsigned int) A->shard_rank)
+    if (heavy_list && tot > A->heavy_tot && t % (unsigned int) A->shard_world == (unsigned int) A->shard_rank)
         heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
     uint4 *dst = reinterpret_cast<uint4 *>(plan + t);
     const uint4 *src = reinterpret_cast<const uint4 *>(&pl);

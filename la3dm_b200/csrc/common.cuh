@@ -114,6 +114,7 @@ struct ScanArgs {
     unsigned int pool_cap;  // block slots allocated
     const float *beam_tab;  // beam_tab[e] = fr + fr + ... (e fp32 additions): distance of beam sample e
     unsigned int beam_tab_n;
+    unsigned int heavy_tot; // test blocks with more neighbourhood points than this are predicted first (kHeavyTot)
 };
 
 // per-scan block grid: restates get_blocks_in_bbox (src/bgkoctomap/bgkoctomap.cpp:486-495) as a Cartesian product of

@@ -346,6 +346,8 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.shard_rank = shard_rank; a.shard_world = shard_world;
         a.n_blocks = (unsigned int) n_blocks; a.pool_cap = (unsigned int) pool_cap;
         a.beam_tab = beam_tab.as<float>(); a.beam_tab_n = kBeamTab;
+        static const unsigned int heavy_tot = getenv("LA3DM_HEAVY_TOT") ? (unsigned int) atoi(getenv("LA3DM_HEAVY_TOT")) : kHeavyTot;
+        a.heavy_tot = heavy_tot;
 
         LA3DM_CUDA(cudaEventRecord(ev0, stream));
         LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));

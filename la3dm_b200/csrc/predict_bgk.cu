@@ -423,6 +423,7 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
     // Work units of 4 test blocks are handed out through one atomic counter.  The heavy blocks (more than kHeavyTot
     // neighbourhood points, listed by k_plan) go first, four of similar weight to a warp; then all test blocks in
     // cell order, the heavy ones skipped.  Test block t belongs to rank t % world.
+    const unsigned int heavy_tot = A->heavy_tot;
     const unsigned int n_heavy = heavy_list ? cnt->n_heavy : 0u;
     const unsigned int heavy_units = (n_heavy + 3u) >> 2;
     const unsigned int T_mine = T > shard_rank ? (T - shard_rank + shard_world - 1u) / shard_world : 0u;
@@ -454,7 +455,7 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
         if (heavy_list && w >= heavy_units) {          // a heavy block met in cell order was done in the first phase
             unsigned int sum = my_count;
             sum += __shfl_xor_sync(full, sum, 1); sum += __shfl_xor_sync(full, sum, 2); sum += __shfl_xor_sync(full, sum, 4);
-            if (sum > kHeavyTot) { have = false; my_count = 0; is_new = 0; }
+            if (sum > heavy_tot) { have = false; my_count = 0; is_new = 0; }
         }
         unsigned int pre = my_count;                                      // inclusive prefix inside the group
 #pragma unroll
