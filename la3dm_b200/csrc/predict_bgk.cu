@@ -543,18 +543,29 @@ k_predict_bgk_oct(const NeighbourPlan *__restrict__ plan, const float4 *__restri
         unsigned int touched = 0;                  // per slot: Occupancy::update ran
 
         // ---- stream the points of the 7 neighbours (ranges concatenated in ExtendedBlock order), 8 per block at a time
-        for (unsigned int base = 0; base < max_tot; base += 8) {
+        // (the next tile's points are requested before the current tile is processed: the load latency hides behind the
+        // support test instead of stalling the warp at the head of every tile)
+        float4 z_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned int nbi_next = 0;
+        auto fetch_tile = [&](unsigned int base) {
             const unsigned int gi = base + (unsigned int) o;
-            const bool valid = gi < tot;
             unsigned int nbi = 0;
 #pragma unroll
             for (int k = 1; k < 7; ++k) nbi += (gi >= __shfl_sync(full, pre, k, 8)) ? 1u : 0u;
             const unsigned int nb_start = __shfl_sync(full, my_start, (int) nbi, 8);
             const unsigned int nb_pre = __shfl_sync(full, pre, (int) nbi, 8);
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            nbi_next = nbi;
+            if (gi < tot) z_next = pts[nb_start + (gi - nb_pre)];
+        };
+        if (max_tot) fetch_tile(0);
+        for (unsigned int base = 0; base < max_tot; base += 8) {
+            const unsigned int gi = base + (unsigned int) o;
+            const bool valid = gi < tot;
+            const unsigned int nbi = nbi_next;
+            float4 z = z_next;
+            if (base + 8 < max_tot) fetch_tile(base + 8);
             bool keep = false;
             if (valid) {
-                z = pts[nb_start + (gi - nb_pre)];
                 const float rx = fmaxf(fabsf(z.x - ccx) - reach, 0.f), ry = fmaxf(fabsf(z.y - ccy) - reach, 0.f),
                             rz = fmaxf(fabsf(z.z - ccz) - reach, 0.f);
                 keep = (rx * rx + (ry * ry + rz * rz)) < cull2;
