@@ -65,6 +65,7 @@ class RefMap:
         L.ref_num_leaves.argtypes = [C.c_void_p]
         L.ref_dump_leaves.argtypes = [C.c_void_p] * 9
         L.ref_get_bbox.argtypes = [C.c_void_p] * 3
+        L.ref_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_training_data.restype = C.c_int64
         L.ref_training_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                                         C.c_float, C.c_void_p]
@@ -119,6 +120,15 @@ class RefMap:
                                             "prob_var")])
         order = np.lexsort((out["index"], out["depth"], out["block_key"]))
         return {k: v[order] for k, v in out.items()}
+
+    def search(self, xyz):
+        """search(x, y, z) for n points -> (ab [n, 2], state [n], classified [n]) of the node upstream returns."""
+        q = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        ab = np.zeros((len(q), 2), np.float32)
+        st = np.zeros(len(q), np.uint8)
+        cl = np.zeros(len(q), np.uint8)
+        self.lib.ref_search(self.h, q.ctypes.data, len(q), ab.ctypes.data, st.ctypes.data, cl.ctypes.data)
+        return ab, st, cl
 
     def get_bbox(self):
         mn = np.zeros(3, np.float32)

@@ -150,6 +150,25 @@ void ref_dump_leaves(void *h, int64_t *block_key, int32_t *depth, int32_t *index
     }
 }
 
+// search(x, y, z) of the reference map (src/bgkoctomap/bgkoctomap.cpp:554-574 -> Block::search, bgkblock.cpp:132-156),
+// n query points: the two node floats, state, classified of the node upstream returns (a default node where the block
+// does not exist).  NOTE upstream's Block::cell_num is frozen at 8 (bgkblock.cpp:105): only meaningful for block_depth 4.
+void ref_search(void *h, const float *xyz, int64_t n, float *ab, uint8_t *state, uint8_t *classified) {
+    MapT *m = static_cast<MapT *>(h);
+    for (int64_t i = 0; i < n; ++i) {
+        la3dm::OcTreeNode node = m->search(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+#if defined(REF_GP)
+        ab[2 * i] = node.m_ivar;
+        ab[2 * i + 1] = node.ivar;
+#else
+        ab[2 * i] = node.m_A;
+        ab[2 * i + 1] = node.m_B;
+#endif
+        state[i] = (uint8_t) node.get_state();
+        classified[i] = node.classified ? 1 : 0;
+    }
+}
+
 void ref_get_bbox(void *h, float *mn, float *mx) {
     point3f a, b;
     static_cast<MapT *>(h)->get_bbox(a, b);

@@ -129,3 +129,50 @@ def test_load_rejects_other_parameters_and_non_empty_maps(scans, tmp_path):
     g.write_bytes(b"not a map file at all, definitely" * 8)
     with pytest.raises(la3dm_b200.La3dmError):
         new_map("bgk").load(str(g))
+
+
+def test_search_agrees_with_the_reference_at_depth_4(scans):
+    """At block_depth 4 upstream's own search is right (Block::cell_num = 8, bgkblock.cpp:105), so the compiled
+    reference is the checker: la3dm_search(finest_only) must name the same finest node, with the same state, as
+    BGKOctoMap::search returns for the same points (tests/test_oracle_golden.py pins what upstream returns)."""
+    from oracle import ref
+    if not ref.available("bgk"):
+        pytest.skip("oracle/_ref not built")
+    from util import oracle_leaves_as_struct
+    pts, org = scans["sim_structured"]
+    p = dict(ref.DEFAULT_PARAMS["bgk"])
+    p["block_depth"] = 4
+    m, r = new_map("bgk", block_depth=4), ref.RefMap("bgk", p)
+    for i in range(4):
+        m.insert_pointcloud(pts[i], org[i], RES, FREE_RES["bgk"], MAX_RANGE)
+        r.insert_pointcloud(pts[i], org[i], RES, FREE_RES["bgk"], MAX_RANGE)
+    want = oracle_leaves_as_struct(r.leaves())
+    rng = np.random.default_rng(11)
+    fin = np.flatnonzero(want["depth"] == 3)
+    pick = rng.choice(fin, 20000, replace=False)
+    off = rng.uniform(-0.45, 0.45, (len(pick), 3)).astype(np.float32) * want["size"][pick, None]
+    q = np.stack([want["x"][pick], want["y"][pick], want["z"][pick]], 1) + off
+    ab, st, _ = r.search(q)
+    assert np.array_equal(ab[:, 0], want["a"][pick]) and np.array_equal(st, want["state"][pick])
+    got = m.search(q, finest_only=True)
+    for k in ("block_key", "depth", "index"):
+        assert np.array_equal(got[k], want[k][pick]), k
+    # the parity bound is on the occupancy probability (1e-4 relative); alpha / beta themselves sit next to the 0.001
+    # priors, where one ulp is already 1.2e-4 relative
+    pw = ab[:, 0].astype(np.float64) / (ab[:, 0].astype(np.float64) + ab[:, 1])
+    np.testing.assert_allclose(got["prob"], pw, rtol=1e-4)
+    np.testing.assert_allclose(got["a"], ab[:, 0], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got["b"], ab[:, 1], rtol=1e-4, atol=1e-6)
+    near = np.abs(want["prob"][pick] - 0.3) < 1e-4
+    near |= np.abs(want["prob"][pick] - 0.7) < 1e-4
+    assert np.array_equal(got["state"][~near], st[~near])
+    # inside pruned leaves upstream hands back the PRUNED finest node; a missing block the default node
+    coarse = np.flatnonzero(want["depth"] < 3)
+    qc = np.stack([want["x"][coarse], want["y"][coarse], want["z"][coarse]], 1) + np.float32(0.01)
+    _, stc, _ = r.search(qc)
+    gc = m.search(qc, finest_only=True)
+    assert (stc == 3).all() and (gc["state"] == 3).all() and (gc["depth"] == 3).all()
+    far = np.array([[300.0, 300.0, 300.0]], np.float32)
+    abf, stf, _ = r.search(far)
+    gf = m.search(far, finest_only=True)
+    assert gf["depth"][0] == -1 and gf["state"][0] == stf[0] == 2 and gf["a"][0] == abf[0, 0] and gf["b"][0] == abf[0, 1]

@@ -122,3 +122,35 @@ def test_edge_cases_empty_and_tiny_clouds():
     # one point: one hit + beam samples
     o.insert_pointcloud(np.float32([[1.0, 0.2, 0.1]]), np.zeros(3, np.float32), RES, 0.5, MAX_RANGE)
     assert o.last_stats()["n_train"] == 5 and o.num_blocks() > 0   # hit + origin + d=0.5, 1.0 + tail l-0.5
+
+
+def test_reference_search_semantics_at_depth_4():
+    """Pins what la3dm_search restates (tests/test_gpu_query.py) on the reference's OWN search
+    (src/bgkoctomap/bgkoctomap.cpp:554-574 -> Block::search, bgkblock.cpp:132-156) at block_depth 4, the one depth for
+    which upstream's frozen Block::cell_num = 8 is right (bgkblock.cpp:105): the node returned for a point is the
+    finest-layer node of the point's cell -- the leaf itself when the leaf is at the finest layer, a PRUNED node inside a
+    pruned leaf -- and a default node where no block exists; `classified` is not copied out (bgkoctree_node.h:36-45)."""
+    from oracle import ref
+    if not ref.available("bgk"):
+        pytest.skip("oracle/_ref not built")
+    z = golden("scans_sim_structured.npz")
+    p = dict(ref.DEFAULT_PARAMS["bgk"])
+    p["block_depth"] = 4
+    r = ref.RefMap("bgk", p, threads=1)
+    for i in range(4):
+        r.insert_pointcloud(z["pts"][i], z["origins"][i], 0.1, 0.5, 8.0)
+    lv = r.leaves()
+    rng = np.random.default_rng(3)
+    fin = np.flatnonzero(lv["depth"] == 3)
+    pick = rng.choice(fin, 20000, replace=False)
+    off = rng.uniform(-0.45, 0.45, (len(pick), 3)).astype(np.float32) * lv["loc_size"][pick, 3:4]
+    ab, st, cl = r.search(lv["loc_size"][pick, :3] + off)
+    assert np.array_equal(ab, lv["ab"][pick]) and np.array_equal(st, lv["state"][pick])
+    del cl      # the copy constructor leaves `classified` uninitialised (bgkoctree_node.h:36-45): indeterminate upstream
+    coarse = np.flatnonzero(lv["depth"] < 3)
+    assert len(coarse) > 0
+    off = rng.uniform(-0.45, 0.45, (len(coarse), 3)).astype(np.float32) * lv["loc_size"][coarse, 3:4]
+    ab, st, cl = r.search(lv["loc_size"][coarse, :3] + off)
+    assert (st == 3).all()                                    # State::PRUNED
+    ab, st, cl = r.search(np.array([[300.0, 300.0, 300.0]], np.float32))
+    assert st[0] == 2 and np.allclose(ab[0], [p["prior_A"], p["prior_B"]])
