@@ -154,3 +154,24 @@ def test_reference_search_semantics_at_depth_4():
     assert (st == 3).all()                                    # State::PRUNED
     ab, st, cl = r.search(np.array([[300.0, 300.0, 300.0]], np.float32))
     assert st[0] == 2 and np.allclose(ab[0], [p["prior_A"], p["prior_B"]])
+
+
+@pytest.mark.skipif(not ref.available("bgk"), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("method,depth", [("bgk", 4), ("bgkl", 5), ("gp", 4)])
+def test_port_against_compiled_reference_at_the_large_map_depths(scans, method, depth):
+    """The -m gpu tests of the `*_large_map.yaml` block depths (BGKL 5, GP 4; BGK 4) use the port as their checker:
+    pin the port on the compiled reference at those depths first."""
+    pts, org = scans["sim_structured" if method != "gp" else "sim_unstructured"]
+    p = dict(ref.DEFAULT_PARAMS[method])
+    p["block_depth"] = depth
+    r, o = ref.RefMap(method, p, threads=1), port.PortMap(method, p)
+    for s in range(2):
+        for m in (r, o):
+            m.insert_pointcloud(pts[s], org[s], RES, FREE_RES[method], MAX_RANGE)
+    got, want = struct(o), oracle_leaves_as_struct(r.leaves())
+    if method == "gp":
+        assert np.array_equal(got["block_key"], want["block_key"]) and np.array_equal(got["index"], want["index"])
+        err = np.abs(got["prob"].astype(np.float64) - want["prob"])
+        assert np.percentile(err, 99) <= 2e-3 and err.max() <= 5e-2
+    else:
+        compare_leaves(got, want, prob_rtol=2e-5, what="%s depth %d" % (method, depth))
