@@ -7,6 +7,40 @@ namespace la3dm_b200 {
 
 constexpr int kRecMax = 672;          // bytes of a depth-3 record: 73 * 8 + 73 -> 16-byte multiple
 
+// sinf(y) and cosf(y) for y in [0, 120), BIT FOR BIT what the host libm returns: glibc >= 2.28 computes them in
+// double precision (ARM optimized-routines sincosf: quadrant n = round(y * 2 / pi) from a 2^24-scaled product,
+// x = y - n * (pi / 2), a degree-7 / degree-8 polynomial pair in double, one rounding to float).  The constants below
+// are the published ones; tests/test_oracle_golden.py::test_sincos_restatement_matches_libm checks a CPU copy of this
+// function against libm on 4e5 arguments of the form  d * 2 * 3.1415926f.  Every product and sum is rounded
+// separately (__dmul_rn / __dadd_rn are never contracted), like the x86-64 baseline build.
+// Why it matters: a voxel seen by one free point flips UNKNOWN -> FREE at k = 1.33e-3 (p = 0.001 / (0.002 + k) < 0.3),
+// a flipped state can complete a group of 8 equal siblings, and a prune changes the leaf SET -- which must stay
+// bit-exact.  With sin / cos identical to the reference's, only the order of the per-leaf additions differs.
+__device__ __forceinline__ void sincosf_libm(float y, float &s, float &c) {
+    const double x0 = (double) y;
+    const int n = (__double2int_rz(__dmul_rn(x0, 0x1.45F306DC9C883p+23)) + 0x800000) >> 24;
+    double x = __dadd_rn(x0, -__dmul_rn((double) n, 0x1.921FB54442D18p0));
+    const double x2 = __dmul_rn(x, x);
+    if (((n + 1) >> 1) & 1) x = -x;                          // sign[n & 3] = {1, -1, -1, 1}
+    // sine polynomial
+    const double x3 = __dmul_rn(x, x2);
+    const double s1 = __dadd_rn(0x1.1107605230bc4p-7, __dmul_rn(x2, -0x1.994eb3774cf24p-13));
+    const double x7 = __dmul_rn(x3, x2);
+    const double sa = __dadd_rn(x, __dmul_rn(x3, -0x1.555545995a603p-3));
+    const double sp = __dadd_rn(sa, __dmul_rn(x7, s1));
+    // cosine polynomial (the table of the quadrants with n & 2 holds the negated coefficients: the result is negated)
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __dadd_rn(-0x1.6c087e89a359dp-10, __dmul_rn(x2, 0x1.99343027bf8c3p-16));
+    const double c1 = __dadd_rn(1.0, __dmul_rn(x2, -0x1.ffffffd0c621cp-2));
+    const double x6 = __dmul_rn(x4, x2);
+    const double ca = __dadd_rn(c1, __dmul_rn(x4, 0x1.55553e1068f19p-5));
+    double cp = __dadd_rn(ca, __dmul_rn(x6, c2));
+    if (n & 2) cp = -cp;
+    const float sf = (float) sp, cf = (float) cp;
+    s = (n & 1) ? cf : sf;                                   // sinf: sinf_poly(x, x2, p, n)
+    c = (n & 1) ? sf : cf;                                   // cosf: sinf_poly(x, x2, p, n ^ 1)
+}
+
 // default record in shared memory: every node = (prior_A, prior_B | 0, min_ivar), UNKNOWN, !classified
 // (bgkoctree_node.h:34 / gpoctree_node.h:34); the spare bytes behind the states are zero except the leaf count
 __device__ __forceinline__ void stage_default_record(uint4 *srec, const DevParams &P, int lane) {

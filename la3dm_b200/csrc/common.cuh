@@ -94,6 +94,10 @@ struct DevParams {
     float noise, l, min_ivar, max_ivar, min_known_ivar;
     int pruned_state;       // 3 (4 for BGKLV)
     float def_a, def_b;     // default node floats: (prior_A, prior_B) or GP (0, min_ivar)
+    // block_depth 3 only: the node-centre LUT is separable per axis (init_key_loc_map, bgkblock.cpp:7-32: bits 4 / 2 / 1
+    // of a child index pick x / y / z at every level) -- ax_off[a][j] = offset on axis a of: j = 0..3 the four finest
+    // coordinates (2 * octant bit + child bit), j = 4, 5 the two depth-1 coordinates, j = 6 the root (0)
+    float ax_off[3][8];
 };
 
 // Arguments of one insert_pointcloud call.  They live in device memory (copied from a pinned host mirror at the head

@@ -194,6 +194,15 @@ void Map::init(int method, const la3dm_params &p, int dev) {
             }
         }
     }
+    if (h.depth == 3) {
+        const int bit[3] = {4, 2, 1};
+        for (int a = 0; a < 3; ++a)
+            for (int j = 0; j < 7; ++j) {
+                const int node = j < 4 ? 9 + 8 * bit[a] * (j >> 1) + bit[a] * (j & 1) : (j < 6 ? 1 + bit[a] * (j - 4) : 0);
+                const float3 o = h_lut[node];
+                h.ax_off[a][j] = a == 0 ? o.x : (a == 1 ? o.y : o.z);
+            }
+    }
     LA3DM_CUDA(cudaMalloc(&d_params, sizeof(DevParams)));
     LA3DM_CUDA(cudaMemcpy(d_params, &h, sizeof(DevParams), cudaMemcpyHostToDevice));
     LA3DM_CUDA(cudaMalloc(&d_lut, sizeof(float3) * h.nodes));

@@ -38,7 +38,7 @@ constexpr int kQCap = 128;            // queue entries per warp; flushed when fe
 __device__ __forceinline__ float sparse_kernel(float d, float sf2) {
     const float t = d * 2.0f * 3.1415926f;
     float s, c;
-    sincosf(t, &s, &c);
+    sincosf_libm(t, s, c);
     float k = (((2.0f + c) * (1.0f - d) / 3.0f) + s / (2.0f * 3.1415926f)) * sf2;
     return k < 0.0f ? 0.0f : k;      // bgkinference.h:120-125
 }
@@ -913,6 +913,392 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     }
 }
 
+
+// ---- k_predict_bgk_flat: block_depth <= 3, ONE warp per test block, the (leaf x point) pair space FLATTENED over the
+// lanes.  On the headline workload only 6 % of the (leaf, training point) pairs of a test block are inside the kernel's
+// support, a block has 33 leaves and 8.5 points that can reach one of them on average, and a quarter of the blocks has
+// none: the cost of a block is its fixed overhead and the idle lanes of whatever is mapped to "one lane per leaf" or
+// "one lane per point".  So:
+//   * the points of the 7 neighbour ranges are read 32 at a time, culled against the hull of the block's leaf centres and
+//     compacted into shared memory; a block without survivors only adds its leaf count to the statistics;
+//   * the block's leaves (is_leaf, bgkoctree.cpp:72-82) are listed once, with their centres already divided by ell
+//     (Block::get_loc + covSparse's  xs / ell, rounded like the reference; block_depth 3: 21 divisions per block through
+//     the per-axis tables, the LUT being separable);
+//   * pair i = leaf (i / S) x survivor (i % S) -- every lane has a pair whatever the shape of the block (1 leaf x 130
+//     points, 64 leaves x 3 points); pairs with d < 1 are appended to a ring in leaf-major order;
+//   * whenever 32 pairs wait, all lanes evaluate the kernel function, one warp-shuffle SEGMENTED scan keyed by the leaf
+//     sums k y and k per leaf, and the last lane of every segment adds the two sums to the leaf's accumulators;
+//   * Occupancy::update (bgkoctree_node.cpp:31-44) runs once per leaf with sum > 0; (m_A, m_B) are read and written in
+//     global memory for those leaves only (a quarter of the visits), the state bytes as 19 words per block.
+// Summation order.  BGKInference::predict returns per neighbour block ybar = Ks y, kbar = rowsum(Ks), and
+// insert_pointcloud applies  if (kbar > 0) update(ybar, kbar)  neighbour after neighbour (bgkoctomap.cpp:314-335).  Every
+// kernel value is >= 0 (bgkinference.h:120-125), so "some neighbour has kbar > 0" is "the sum over all neighbours is
+// > 0", and a neighbour with kbar == 0 adds nothing: m_A += sum k y, m_B += sum k - sum k y over the whole
+// ExtendedBlock differs from the reference only in the association of the fp32 additions (the reference itself sums in
+// R-tree order).  The order used here is fixed by the input alone (ring position), so results are reproducible and
+// identical on every replica; parity against the compiled reference is checked at 1e-4 on the probability.
+constexpr int kFlatWarps = 8;
+constexpr int kFlatPts = 64;          // survivors staged per chunk
+constexpr int kFlatQ = 64;            // ring capacity (in-support pairs waiting for evaluation)
+#ifndef LA3DM_FLAT_MIN_CTAS
+#define LA3DM_FLAT_MIN_CTAS 4
+#endif
+
+struct FlatSmem {
+    float4 leaf[64];                  // centre / ell of the block's leaves; .w = node index (bits)
+    float4 pt[kFlatPts];              // survivors of the hull cull: (x / ell, y / ell, z / ell, label)
+    float2 acc[64];                   // per leaf: (sum k y, sum k)
+    float2 q[kFlatQ];                 // ring: (squared distance, label)
+    unsigned int st[20];              // state bytes of the record and the spare bytes behind them, as words
+    float tab[3][8];                  // per axis: (LUT offset + block centre) / ell of the 4 + 2 + 1 coordinates
+    unsigned char ql[kFlatQ];         // ring: leaf position of the pair
+};
+static_assert(sizeof(FlatSmem) % 16 == 0, "per-warp slices stay 16-byte aligned");
+
+// covSparse element for a squared distance in [0, 1) (already in units of ell): bgkinference.h:115-126 with the
+// reference's constants, order of operations and roundings (IEEE sqrt and divisions, libm's sin / cos)
+__device__ __forceinline__ float sparse_kernel_d2(float d2, float sf2) {
+    const float d = sqrtf(d2);
+    const float t = d * 2.0f * 3.1415926f;
+    float s, c;
+    sincosf_libm(t, s, c);
+    const float k = (((2.0f + c) * (1.0f - d) / 3.0f) + s / (2.0f * 3.1415926f)) * sf2;
+    return k < 0.0f ? 0.0f : k;      // bgkinference.h:120-125
+}
+
+template <bool kD3>
+__global__ void __launch_bounds__(kFlatWarps * 32, LA3DM_FLAT_MIN_CTAS)
+k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
+                   const long long *__restrict__ keys, unsigned char *__restrict__ pool,
+                   const float3 *__restrict__ lut, const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A,
+                   ScanCounters *cnt, const unsigned int *__restrict__ heavy_list) {
+    __shared__ __align__(16) FlatSmem sm[kFlatWarps];
+    __shared__ DevParams Ps;
+    if (threadIdx.x < sizeof(DevParams) / 4)
+        reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    __syncthreads();
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int full = 0xffffffffu, lt = (1u << lane) - 1u;
+    FlatSmem &S = sm[warp];
+    unsigned char *sst = reinterpret_cast<unsigned char *>(S.st);
+    const unsigned int T = cnt->n_test_blocks;
+    const int D = kD3 ? 3 : P.depth;
+    const int nodes = kD3 ? 73 : P.nodes, st_off = kD3 ? 584 : P.st_off, rec_bytes = kD3 ? 672 : P.rec_bytes;
+    const int nst_words = (nodes + 4) >> 2;                  // state bytes + the leaf-count byte behind them
+    const int l1 = kD3 ? 1 : P.layer_off[1], l2 = kD3 ? 9 : (D > 2 ? P.layer_off[2] : 0x7fffffff);
+    const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
+    const float inv_ell = 1.0f / ell;
+    const float occ_t = P.occupied_thresh, free_t = P.free_thresh, var_t = P.var_thresh;
+    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
+    // every leaf centre lies within (block_size - resolution) / 2 of the block centre (conservative, in units of ell)
+    const float reach = 0.5f * (bs - P.resolution) * 1.001f / ell;
+    const float cull2 = 1.0f + 1e-4f;
+
+    unsigned int visits = 0, updates = 0;
+    unsigned long long pairs = 0;
+
+    // Work units come from one atomic counter: first the heavy blocks (more than heavy_tot neighbourhood points, listed
+    // by k_plan), one per unit, then units of kUnit consecutive test blocks of this rank (t % world == rank), the heavy
+    // ones skipped.
+    constexpr unsigned int kUnit = 4;
+    const unsigned int heavy_tot = A->heavy_tot;
+    const unsigned int n_heavy = heavy_list ? cnt->n_heavy : 0u;
+    const unsigned int T_mine = T > shard_rank ? (T - shard_rank + shard_world - 1u) / shard_world : 0u;
+    const unsigned int units = n_heavy + (T_mine + kUnit - 1u) / kUnit;
+    unsigned int w_next = 0;
+    if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);
+    for (;;) {
+        const unsigned int w = __shfl_sync(full, w_next, 0);
+        if (w >= units) break;
+        if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);          // in flight while this unit is processed
+        const bool heavy_unit = w < n_heavy;
+        const unsigned int n_in_unit = heavy_unit ? 1u : kUnit;
+#pragma unroll 1
+        for (unsigned int j = 0; j < n_in_unit; ++j) {
+            unsigned int t;
+            if (heavy_unit) t = heavy_list[w];
+            else {
+                t = (kUnit * (w - n_heavy) + j) * shard_world + shard_rank;
+                if (t >= T) break;
+            }
+            // ---- plan: lanes 0..6 hold start / count of one neighbour each
+            const unsigned int plw = lane < 16 ? reinterpret_cast<const unsigned int *>(plan + t)[lane] : 0u;
+            const unsigned int my_start = plw;
+            unsigned int my_count = __shfl_down_sync(full, plw, 7);
+            if (lane >= 7) my_count = 0u;
+            const unsigned int slot = __shfl_sync(full, plw, 14), is_new = __shfl_sync(full, plw, 15);
+            unsigned int pre = my_count;                                  // inclusive prefix over lanes 0..6
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const unsigned int up = __shfl_up_sync(full, pre, o);
+                if (lane >= o) pre += up;
+            }
+            const unsigned int tot = __shfl_sync(full, pre, 6);
+            if (!heavy_unit && heavy_list && tot > heavy_tot) continue;   // done in the first phase
+            pre -= my_count;                                              // exclusive
+            const unsigned int delta = my_start - pre;                    // point gi of neighbour k sits at gi + delta_k
+            unsigned char *rec = pool + (size_t) slot * (size_t) rec_bytes;
+            float2 *gab = reinterpret_cast<float2 *>(rec);
+            unsigned int *gst = reinterpret_cast<unsigned int *>(rec + st_off);
+            // ---- state bytes (a fresh Block: the default node everywhere, bgkoctree_node.h:34; its record is written now)
+            unsigned int stw = 0;
+            if (is_new) {
+                for (int n = lane; n < nodes; n += 32) gab[n] = make_float2(P.def_a, P.def_b);
+                if (lane < nst_words) {
+                    stw = 0x02020202u;                                    // LA3DM_UNKNOWN x 4
+                    const int b0 = 4 * lane;                              // bytes b0 .. b0 + 3 of the state area
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (b0 + b >= nodes)
+                            stw = (stw & ~(0xFFu << (8 * b))) | ((b0 + b == nodes ? (unsigned int) (P.finest & 0xFF) : 0u) << (8 * b));
+                    gst[lane] = stw;
+                }
+            } else if (lane < nst_words) stw = gst[lane];
+            const long long key = keys[slot];
+            // ---- 32 points of the neighbourhood (ranges concatenated in ExtendedBlock order)
+            auto fetch = [&](unsigned int base, float4 &z) -> bool {
+                const unsigned int gi = base + (unsigned int) lane;
+                unsigned int nbi = 0;
+#pragma unroll
+                for (int k = 1; k < 7; ++k) nbi += (gi >= __shfl_sync(full, pre, k)) ? 1u : 0u;
+                const unsigned int d = __shfl_sync(full, delta, (int) nbi);
+                if (gi < tot) { z = pts[gi + d]; return true; }
+                return false;
+            };
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool valid = fetch(0, z);
+            // block centre from its key (hash_key_to_block, bgkblock.cpp:79-83); the hull test may round differently
+            const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
+                        cz = axis_center(key & 0xFFFFF, bs);
+            const float ccx = cx * inv_ell, ccy = cy * inv_ell, ccz = cz * inv_ell;
+            __syncwarp();
+            if (lane < nst_words) S.st[lane] = stw;
+            int Lf = -1;                                                  // leaves listed (-1: not yet)
+            unsigned int qh = 0, qt = 0;                                  // ring head / tail (monotonic; position = & 63)
+
+            // evaluates `c` (<= 32) waiting pairs: kernel value by all lanes, segmented sums per leaf, accumulate
+            auto drain = [&](unsigned int c) {
+                __syncwarp();
+                const unsigned int pos = (qh + (unsigned int) lane) & (kFlatQ - 1);
+                const bool e = (unsigned int) lane < c;
+                float vy = 0.f, vk = 0.f;
+                unsigned int lp = 0xFFu;
+                if (e) {
+                    const float2 dq = S.q[pos];
+                    lp = S.ql[pos];
+                    vk = sparse_kernel_d2(dq.x, sf2);
+                    vy = vk * dq.y;
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float ty = __shfl_up_sync(full, vy, o), tk = __shfl_up_sync(full, vk, o);
+                    const unsigned int tl = __shfl_up_sync(full, lp, o);
+                    if (lane >= o && tl == lp) { vy += ty; vk += tk; }
+                }
+                const unsigned int nl = __shfl_down_sync(full, lp, 1);
+                if (e && (lane == 31 || nl != lp)) {
+                    float2 a = S.acc[lp];
+                    a.x += vy; a.y += vk;
+                    S.acc[lp] = a;
+                }
+                qh += c;
+                __syncwarp();
+            };
+
+            unsigned int ns = 0;                                          // survivors staged in S.pt
+#pragma unroll 1
+            for (unsigned int base = 0; base < tot; base += 32) {
+                if (base) valid = fetch(base, z);
+                bool keep = false;
+                if (valid) {
+                    const float rx = fmaxf(fabsf(z.x - ccx) - reach, 0.f), ry = fmaxf(fabsf(z.y - ccy) - reach, 0.f),
+                                rz = fmaxf(fabsf(z.z - ccz) - reach, 0.f);
+                    keep = (rx * rx + (ry * ry + rz * rz)) < cull2;
+                }
+                const unsigned int kept = __ballot_sync(full, keep);
+                if (keep) S.pt[ns + __popc(kept & lt)] = z;
+                ns += __popc(kept);
+                const bool last = base + 32 >= tot;
+                if (ns == 0 || (!last && ns <= (unsigned int) (kFlatPts - 32))) continue;
+                // ---- list the block's leaves once: centre / ell and node index; zero their accumulators
+                if (Lf < 0) {
+                    if (kD3) {
+                        if (lane < 21) {
+                            const int a = lane / 7, jj = lane - 7 * a;
+                            const float c = a == 0 ? cx : (a == 1 ? cy : cz);
+                            S.tab[a][jj] = (P.ax_off[a][jj] + c) / ell;
+                        }
+                    }
+                    __syncwarp();
+                    Lf = 0;
+                    if (kD3) {
+                        // lane: finest voxels 9 + lane and 9 + 32 + lane, then (lanes 0..8) the nine coarse nodes
+#pragma unroll
+                        for (int h = 0; h < 3; ++h) {
+                            const int n = h < 2 ? 9 + 32 * h + lane : lane;
+                            bool leaf = false;
+                            if (h < 2) leaf = (sst[n] & 7) != kStPRUNED;
+                            else if (lane < 9) leaf = (sst[n] & 7) != kStPRUNED && (sst[lane == 0 ? 1 : 1 + 8 * lane] & 7) == kStPRUNED;
+                            const unsigned int m = __ballot_sync(full, leaf);
+                            if (leaf) {
+                                const int pos = Lf + __popc(m & lt);
+                                int xj, yj, zj;
+                                if (h < 2) {
+                                    xj = 2 * h + ((lane >> 2) & 1); yj = ((lane >> 3) & 2) | ((lane >> 1) & 1);
+                                    zj = ((lane >> 2) & 2) | (lane & 1);
+                                } else if (lane > 0) { const int i = lane - 1; xj = 4 + ((i >> 2) & 1); yj = 4 + ((i >> 1) & 1); zj = 4 + (i & 1); }
+                                else { xj = yj = zj = 6; }
+                                S.leaf[pos] = make_float4(S.tab[0][xj], S.tab[1][yj], S.tab[2][zj], __int_as_float(n));
+                                S.acc[pos] = make_float2(0.f, 0.f);
+                            }
+                            Lf += __popc(m);
+                        }
+                    } else {
+                        for (int n0 = 0; n0 < nodes; n0 += 32) {
+                            const int n = n0 + lane;
+                            bool leaf = false;
+                            if (n < nodes) {
+                                const int d = n >= l2 ? 2 : (n >= l1 ? 1 : 0);
+                                const int i = n - P.layer_off[d];
+                                leaf = (sst[n] & 7) != kStPRUNED &&
+                                       (d == D - 1 || (sst[P.layer_off[d + 1] + 8 * i] & 7) == kStPRUNED);
+                            }
+                            const unsigned int m = __ballot_sync(full, leaf);
+                            if (leaf) {
+                                const int pos = Lf + __popc(m & lt);
+                                // Block::get_loc: LUT offset + centre, then covSparse's  xs / ell
+                                const float3 off = lut[n];
+                                S.leaf[pos] = make_float4((off.x + cx) / ell, (off.y + cy) / ell, (off.z + cz) / ell,
+                                                          __int_as_float(n));
+                                S.acc[pos] = make_float2(0.f, 0.f);
+                            }
+                            Lf += __popc(m);
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- the chunk's pairs, leaf-major: pair i = leaf i / ns, survivor i % ns; each lane walks i = lane,
+                // lane + 32, ... keeping (leaf, survivor) incrementally
+                const unsigned int np = (unsigned int) Lf * ns;
+                const unsigned int q32 = 32u / ns, r32 = 32u - q32 * ns;
+                unsigned int lp = (unsigned int) lane / ns, pi = (unsigned int) lane - lp * ns;
+#pragma unroll 1
+                for (unsigned int i0 = 0; i0 < np; i0 += 32) {
+                    bool in = false;
+                    float d2 = 0.f, yv = 0.f;
+                    if (i0 + (unsigned int) lane < np) {
+                        const float4 L = S.leaf[lp], pq = S.pt[pi];
+                        const float dx = pq.x - L.x, dy = pq.y - L.y, dz = pq.z - L.z;
+                        d2 = dx * dx + (dy * dy + dz * dz);      // Eigen rowwise().norm() of a 3-vector, squared
+                        yv = pq.w;
+                        in = d2 < 1.0f;                          // k <= 0 for d >= 1 (clamped upstream)
+                    }
+                    const unsigned int m = __ballot_sync(full, in);
+                    if (m != 0u) {
+                        if (in) {
+                            const unsigned int pos = (qt + __popc(m & lt)) & (kFlatQ - 1);
+                            S.q[pos] = make_float2(d2, yv);
+                            S.ql[pos] = (unsigned char) lp;
+                        }
+                        qt += __popc(m);
+                        if (qt - qh >= 32u) drain(32u);
+                    }
+                    lp += q32; pi += r32;
+                    if (pi >= ns) { pi -= ns; ++lp; }
+                }
+                if (qt != qh) drain(qt - qh);
+                ns = 0;
+                __syncwarp();
+            }
+            // ---- statistics; a block no training point can reach is done (its leaf count sits behind the states)
+            if (Lf < 0) {
+                const unsigned int wl = __shfl_sync(full, stw, nodes >> 2);
+                const unsigned int n_leaves = (wl >> (8 * (nodes & 3))) & 0xFFu;
+                if (lane == 0) { visits += n_leaves; pairs += (unsigned long long) n_leaves * tot; }
+                continue;
+            }
+            if (lane == 0) { visits += (unsigned int) Lf; pairs += (unsigned long long) Lf * tot; }
+            // ---- Occupancy::update (bgkoctree_node.cpp:31-44) for the leaves with kbar > 0 (bgkoctomap.cpp:332)
+            bool changed = false, touched_any = false;
+#pragma unroll 1
+            for (int lp0 = 0; lp0 < Lf; lp0 += 32) {
+                const int lq = lp0 + lane;
+                if (lq < Lf) {
+                    const float2 s = S.acc[lq];
+                    if (s.y > 0.0f) {
+                        const int n = __float_as_int(S.leaf[lq].w);
+                        float2 ab = gab[n];
+                        ab.x += s.x;
+                        ab.y += s.y - s.x;
+                        gab[n] = ab;
+                        // get_var (bgkoctree_node.h:60) is below 1/4 for any (m_A, m_B) > 0: only evaluated if it can matter
+                        unsigned int ns_ = LA3DM_UNKNOWN;
+                        bool known = true;
+                        if (var_t < 0.25f) known = !((ab.x * ab.y) / ((ab.x + ab.y) * (ab.x + ab.y) * (ab.x + ab.y + 1.0f)) > var_t);
+                        if (known) {
+                            const float p = ab.x / (ab.x + ab.y);
+                            ns_ = p > occ_t ? LA3DM_OCCUPIED : (p < free_t ? LA3DM_FREE : LA3DM_UNKNOWN);
+                        }
+                        const unsigned int old = sst[n];
+                        sst[n] = (unsigned char) (ns_ | 0x80u);   // classified = true
+                        changed = changed || ((old & 7u) != ns_);
+                        touched_any = true;
+                        ++updates;
+                    }
+                }
+            }
+            if (!__any_sync(full, touched_any)) continue;
+            __syncwarp();
+            // ---- OcTree::prune (bgkoctree.cpp:101-148): only a state that changed can complete a group of 8 equal siblings
+            if (__any_sync(full, changed)) {
+                bool pruned = false;
+                for (int d = D - 1; d > 0; --d) {
+                    const int off = P.layer_off[d], poff = P.layer_off[d - 1];
+                    const int groups = 1 << (3 * (d - 1));
+                    for (int g = lane; g < groups; g += 32) {
+                        const unsigned char s0 = sst[off + 8 * g] & 7;
+                        if (s0 == LA3DM_FREE || s0 == LA3DM_OCCUPIED) {
+                            bool same = true;
+#pragma unroll
+                            for (int i = 1; i < 8; ++i) same = same && ((sst[off + 8 * g + i] & 7) == s0);
+                            if (same) {
+                                gab[poff + g] = __ldcg(&gab[off + 8 * g]);    // parent := child 0 (classified is not copied)
+                                sst[poff + g] = (sst[poff + g] & 0x80) | s0;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) sst[off + 8 * g + i] = (sst[off + 8 * g + i] & 0x80) | kStPRUNED;
+                                pruned = true;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (__any_sync(full, pruned)) {
+                    const int n_leaves = count_leaves(sst, P, lane);
+                    if (lane == 0) sst[nodes] = (unsigned char) n_leaves;
+                    __syncwarp();
+                }
+            }
+            if (lane < nst_words) gst[lane] = S.st[lane];
+        }
+    }
+
+    // stats: one atomic per warp
+    unsigned long long v64 = visits, u64 = updates;
+    for (int d = 16; d > 0; d >>= 1) {
+        v64 += __shfl_xor_sync(full, v64, d);
+        u64 += __shfl_xor_sync(full, u64, d);
+        pairs += __shfl_xor_sync(full, pairs, d);
+    }
+    if (lane == 0 && v64) {
+        atomicAdd(&cnt->visits, v64);
+        atomicAdd(&cnt->updates, u64);
+        atomicAdd(&cnt->pairs, pairs);
+    }
+}
+
+
 }  // namespace
 
 void Map::enqueue_predict() {
@@ -920,7 +1306,18 @@ void Map::enqueue_predict() {
     const int ctas = num_sms * 4;
     static const bool force_v1 = getenv("LA3DM_PREDICT_V1") != nullptr;     // debugging: the one-warp-per-block kernel
     record_event(ev_p0);
-    if (hp.depth == 3 && !force_v1) {
+    static const bool force_oct = getenv("LA3DM_PREDICT_OCT") != nullptr;   // A/B: round 1's eight-lanes-per-block kernel
+    if (hp.depth <= 3 && !force_v1 && !force_oct) {
+        auto kern = hp.depth == 3 ? k_predict_bgk_flat<true> : k_predict_bgk_flat<false>;
+        int occ = 0;
+        LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFlatWarps * 32, 0));
+        if (occ < 1) occ = 1;
+        kern<<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(
+            plan.as<NeighbourPlan>(), pts_sorted.as<float4>(), keys.as<long long>(), pool.as<unsigned char>(), d_lut,
+            d_params, d_args, d_cnt, getenv("LA3DM_OCT_NO_HEAVY") ? nullptr : heavy_list.as<unsigned int>());
+        LA3DM_CUDA(cudaGetLastError());
+    }
+    else if (hp.depth == 3 && !force_v1) {
         static const int oct_ctas = getenv("LA3DM_OCT_CTAS") ? atoi(getenv("LA3DM_OCT_CTAS")) : 2;
         const int n = oct_ctas == 1 ? 1 : 2;
         auto kern = n == 1 ? k_predict_bgk_oct<1> : k_predict_bgk_oct<2>;

@@ -175,3 +175,36 @@ def test_port_against_compiled_reference_at_the_large_map_depths(scans, method, 
         assert np.percentile(err, 99) <= 2e-3 and err.max() <= 5e-2
     else:
         compare_leaves(got, want, prob_rtol=2e-5, what="%s depth %d" % (method, depth))
+
+
+def test_sincos_restatement_matches_libm():
+    """la3dm_b200/csrc/block_common.cuh:sincosf_libm restates glibc's sinf / cosf (double-precision polynomial pair of
+    ARM optimized-routines, one rounding to float) so that the CUDA kernel values equal the compiled reference's bit
+    for bit; this checks a numpy copy of the same arithmetic against the host libm on arguments of the form
+    d * 2 * 3.1415926f, d in [0, 1) (bgkinference.h:115-116)."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    for f in (libm.sinf, libm.cosf):
+        f.restype, f.argtypes = C.c_float, [C.c_float]
+    H = float.fromhex
+    hpi_inv, hpi = H("0x1.45F306DC9C883p+23"), H("0x1.921FB54442D18p0")
+    c1, c2, c3, c4 = H("-0x1.ffffffd0c621cp-2"), H("0x1.55553e1068f19p-5"), H("-0x1.6c087e89a359dp-10"), H("0x1.99343027bf8c3p-16")
+    s1, s2, s3 = H("-0x1.555545995a603p-3"), H("0x1.1107605230bc4p-7"), H("-0x1.994eb3774cf24p-13")
+    rng = np.random.default_rng(5)
+    d = np.concatenate([rng.random(60000), 1.0 - rng.random(20000) * 1e-3, rng.random(20000) * 1e-3]).astype(np.float32)
+    y = (d * np.float32(2.0) * np.float32(3.1415926)).astype(np.float32)
+    x0 = y.astype(np.float64)
+    n = ((x0 * hpi_inv).astype(np.int32).astype(np.int64) + 0x800000) >> 24
+    x = x0 - n * hpi
+    x2 = x * x
+    x = np.where(((n + 1) >> 1) & 1, -x, x)
+    x3 = x * x2
+    sp = (x + x3 * s1) + (x3 * x2) * (s2 + x2 * s3)
+    x4 = x2 * x2
+    cp = ((1.0 + x2 * c1) + x4 * c2) + (x4 * x2) * (c3 + x2 * c4)
+    cp = np.where(n & 2, -cp, cp)
+    sf, cf = sp.astype(np.float32), cp.astype(np.float32)
+    got_s, got_c = np.where(n & 1, cf, sf), np.where(n & 1, sf, cf)
+    want_s = np.array([libm.sinf(float(v)) for v in y], np.float32)
+    want_c = np.array([libm.cosf(float(v)) for v in y], np.float32)
+    assert np.array_equal(got_s, want_s) and np.array_equal(got_c, want_c)
