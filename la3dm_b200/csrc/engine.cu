@@ -430,6 +430,11 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     stats.replays = call_replays;
     stats.graph_captures = call_captures;
     stats.grid_irregular = (int32_t) h_cnt->grid_irregular;
+#ifdef LA3DM_FLAT_STATS
+    fprintf(stderr, "flat stats: blocks %u chunks %u surv %u np %u iters %u in %u drains %u (long/mid run counters included)\n",
+            h_cnt->pad2_, h_cnt->n_long_runs[1], h_cnt->n_mid_runs[1], h_cnt->vg_cells_needed, h_cnt->n_long_runs[0],
+            h_cnt->reserved_, h_cnt->n_mid_runs[0]);
+#endif
     stats.h2d_bytes = h2d_bytes + (long long) sizeof(ScanArgs);   // h2d_bytes: the cloud, set by the host entry point
     stats.d2h_bytes = d2h_bytes;
     h2d_bytes = 0;

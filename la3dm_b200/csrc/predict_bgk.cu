@@ -939,7 +939,7 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
 // identical on every replica; parity against the compiled reference is checked at 1e-4 on the probability.
 constexpr int kFlatWarps = 8;
 constexpr int kFlatPts = 64;          // survivors staged per chunk
-constexpr int kFlatQ = 64;            // ring capacity (in-support pairs waiting for evaluation)
+constexpr int kFlatQ = 128;           // ring capacity (in-support pairs waiting for evaluation; <= 31 + 64 at a time)
 #ifndef LA3DM_FLAT_MIN_CTAS
 #define LA3DM_FLAT_MIN_CTAS 4
 #endif
@@ -998,6 +998,9 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
 
     unsigned int visits = 0, updates = 0;
     unsigned long long pairs = 0;
+#ifdef LA3DM_FLAT_STATS
+    unsigned int dbg_it = 0, dbg_chunks = 0, dbg_drains = 0, dbg_surv = 0, dbg_in = 0, dbg_blocks = 0, dbg_np = 0;
+#endif
 
     // Work units come from one atomic counter: first the heavy blocks (more than heavy_tot neighbourhood points, listed
     // by k_plan), one per unit, then units of kUnit consecutive test blocks of this rank (t % world == rank), the heavy
@@ -1039,6 +1042,9 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             if (!heavy_unit && heavy_list && tot > heavy_tot) continue;   // done in the first phase
             pre -= my_count;                                              // exclusive
             const unsigned int delta = my_start - pre;                    // point gi of neighbour k sits at gi + delta_k
+#ifdef LA3DM_FLAT_STATS
+            ++dbg_blocks;
+#endif
             unsigned char *rec = pool + (size_t) slot * (size_t) rec_bytes;
             float2 *gab = reinterpret_cast<float2 *>(rec);
             unsigned int *gst = reinterpret_cast<unsigned int *>(rec + st_off);
@@ -1081,6 +1087,9 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             // evaluates `c` (<= 32) waiting pairs: kernel value by all lanes, segmented sums per leaf, accumulate
             auto drain = [&](unsigned int c) {
                 __syncwarp();
+#ifdef LA3DM_FLAT_STATS
+                ++dbg_drains;
+#endif
                 const unsigned int pos = (qh + (unsigned int) lane) & (kFlatQ - 1);
                 const bool e = (unsigned int) lane < c;
                 float vy = 0.f, vk = 0.f;
@@ -1182,31 +1191,54 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 // ---- the chunk's pairs, leaf-major: pair i = leaf i / ns, survivor i % ns; each lane walks i = lane,
                 // lane + 32, ... keeping (leaf, survivor) incrementally
                 const unsigned int np = (unsigned int) Lf * ns;
+#ifdef LA3DM_FLAT_STATS
+                ++dbg_chunks; dbg_surv += ns; dbg_np += np;
+#endif
+                // (two pairs per lane and trip, i and i + 32: independent distance computations behind one loop overhead)
                 const unsigned int q32 = 32u / ns, r32 = 32u - q32 * ns;
-                unsigned int lp = (unsigned int) lane / ns, pi = (unsigned int) lane - lp * ns;
+                const unsigned int w64 = 2u * r32 >= ns ? 1u : 0u, q64 = 2u * q32 + w64, r64 = 2u * r32 - w64 * ns;
+                unsigned int lpA = (unsigned int) lane / ns, piA = (unsigned int) lane - lpA * ns;
+                unsigned int lpB = lpA + q32, piB = piA + r32;
+                if (piB >= ns) { piB -= ns; ++lpB; }
 #pragma unroll 1
-                for (unsigned int i0 = 0; i0 < np; i0 += 32) {
-                    bool in = false;
-                    float d2 = 0.f, yv = 0.f;
-                    if (i0 + (unsigned int) lane < np) {
-                        const float4 L = S.leaf[lp], pq = S.pt[pi];
+                for (unsigned int i0 = (unsigned int) lane; i0 < np + (unsigned int) lane; i0 += 64) {
+                    float dA = 2.f, dB = 2.f, yA = 0.f, yB = 0.f;
+                    if (i0 < np) {
+                        const float4 L = S.leaf[lpA], pq = S.pt[piA];
                         const float dx = pq.x - L.x, dy = pq.y - L.y, dz = pq.z - L.z;
-                        d2 = dx * dx + (dy * dy + dz * dz);      // Eigen rowwise().norm() of a 3-vector, squared
-                        yv = pq.w;
-                        in = d2 < 1.0f;                          // k <= 0 for d >= 1 (clamped upstream)
+                        dA = dx * dx + (dy * dy + dz * dz);      // Eigen rowwise().norm() of a 3-vector, squared
+                        yA = pq.w;
                     }
-                    const unsigned int m = __ballot_sync(full, in);
-                    if (m != 0u) {
-                        if (in) {
-                            const unsigned int pos = (qt + __popc(m & lt)) & (kFlatQ - 1);
-                            S.q[pos] = make_float2(d2, yv);
-                            S.ql[pos] = (unsigned char) lp;
+                    if (i0 + 32u < np) {
+                        const float4 L = S.leaf[lpB], pq = S.pt[piB];
+                        const float dx = pq.x - L.x, dy = pq.y - L.y, dz = pq.z - L.z;
+                        dB = dx * dx + (dy * dy + dz * dz);
+                        yB = pq.w;
+                    }
+                    const bool inA = dA < 1.0f, inB = dB < 1.0f;     // k <= 0 for d >= 1 (clamped upstream)
+                    const unsigned int mA = __ballot_sync(full, inA), mB = __ballot_sync(full, inB);
+#ifdef LA3DM_FLAT_STATS
+                    ++dbg_it; dbg_in += __popc(mA) + __popc(mB);
+#endif
+                    if ((mA | mB) != 0u) {
+                        const unsigned int cA = __popc(mA);
+                        if (inA) {
+                            const unsigned int pos = (qt + __popc(mA & lt)) & (kFlatQ - 1);
+                            S.q[pos] = make_float2(dA, yA);
+                            S.ql[pos] = (unsigned char) lpA;
                         }
-                        qt += __popc(m);
-                        if (qt - qh >= 32u) drain(32u);
+                        if (inB) {
+                            const unsigned int pos = (qt + cA + __popc(mB & lt)) & (kFlatQ - 1);
+                            S.q[pos] = make_float2(dB, yB);
+                            S.ql[pos] = (unsigned char) lpB;
+                        }
+                        qt += cA + __popc(mB);
+                        while (qt - qh >= 32u) drain(32u);
                     }
-                    lp += q32; pi += r32;
-                    if (pi >= ns) { pi -= ns; ++lp; }
+                    lpA += q64; piA += r64;
+                    if (piA >= ns) { piA -= ns; ++lpA; }
+                    lpB += q64; piB += r64;
+                    if (piB >= ns) { piB -= ns; ++lpB; }
                 }
                 if (qt != qh) drain(qt - qh);
                 ns = 0;
@@ -1253,10 +1285,12 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             __syncwarp();
             // ---- OcTree::prune (bgkoctree.cpp:101-148): only a state that changed can complete a group of 8 equal siblings
             if (__any_sync(full, changed)) {
-                bool pruned = false;
+                int n_pruned_groups = 0;
+                bool root_pruned = false;
                 for (int d = D - 1; d > 0; --d) {
                     const int off = P.layer_off[d], poff = P.layer_off[d - 1];
                     const int groups = 1 << (3 * (d - 1));
+                    bool did = false;
                     for (int g = lane; g < groups; g += 32) {
                         const unsigned char s0 = sst[off + 8 * g] & 7;
                         if (s0 == LA3DM_FREE || s0 == LA3DM_OCCUPIED) {
@@ -1268,17 +1302,18 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                                 sst[poff + g] = (sst[poff + g] & 0x80) | s0;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) sst[off + 8 * g + i] = (sst[off + 8 * g + i] & 0x80) | kStPRUNED;
-                                pruned = true;
+                                did = true;
                             }
                         }
                     }
+                    n_pruned_groups += __popc(__ballot_sync(full, did));      // (groups <= 32 per layer for block_depth <= 3)
+                    if (d == 1) root_pruned = __any_sync(full, did);
                     __syncwarp();
                 }
-                if (__any_sync(full, pruned)) {
-                    const int n_leaves = count_leaves(sst, P, lane);
-                    if (lane == 0) sst[nodes] = (unsigned char) n_leaves;
-                    __syncwarp();
-                }
+                // every collapsed group turns 8 leaves into 1
+                if (n_pruned_groups && lane == 0) sst[nodes] = (unsigned char) (Lf - 7 * n_pruned_groups);
+                (void) root_pruned;
+                __syncwarp();
             }
             if (lane < nst_words) gst[lane] = S.st[lane];
         }
@@ -1296,6 +1331,13 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
         atomicAdd(&cnt->updates, u64);
         atomicAdd(&cnt->pairs, pairs);
     }
+#ifdef LA3DM_FLAT_STATS
+    if (lane == 0) {
+        atomicAdd(&cnt->n_long_runs[0], dbg_it); atomicAdd(&cnt->n_long_runs[1], dbg_chunks);
+        atomicAdd(&cnt->n_mid_runs[0], dbg_drains); atomicAdd(&cnt->n_mid_runs[1], dbg_surv);
+        atomicAdd(&cnt->reserved_, dbg_in); atomicAdd(&cnt->pad2_, dbg_blocks); atomicAdd(&cnt->vg_cells_needed, dbg_np);
+    }
+#endif
 }
 
 

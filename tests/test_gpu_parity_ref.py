@@ -39,15 +39,18 @@ def _dist(err):
 
 @needs_ref
 def test_headline_workload_matches_compiled_reference():
-    """The workload bench.py times (bgkoctomap.yaml, 65 536 points, 50 m, seed 1): 4 overlapping scans into the GPU map
+    """The workload bench.py times (bgkoctomap.yaml, 65 536 points, 50 m, seed 1): 3 overlapping scans into the GPU map
     and into the compiled reference, compared leaf by leaf after every scan (src/bgkoctomap/bgkoctomap.cpp:214-366)."""
     import bench
     import la3dm_b200
     from la3dm_b200.synthetic import make_sequence
-    n = 4
+    n = 3
     pts, org = make_sequence(n, 65536, 50.0, 1)
     m = la3dm_b200.BGKOctoMap(**bench.BGK)
-    r = ref.RefMap("bgk", dict(bench.BGK), fast=False, threads=os.cpu_count())
+    # ONE host thread: upstream reads block_arr[key] outside its critical section (bgkoctomap.cpp:298-305) while other
+    # threads insert into the same unordered_map -- with dozens of threads and 1.4e5 new blocks per scan that latent race
+    # does lose updates now and then, and the checker must be deterministic
+    r = ref.RefMap("bgk", dict(bench.BGK), fast=False, threads=1)
     out = []
     for s in range(n):
         m.insert_pointcloud(pts[s], org[s], bench.DS_RES, bench.FREE_RES, bench.MAX_RANGE)
