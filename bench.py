@@ -170,7 +170,8 @@ def ref_available():
 def time_reference(pts, org, scan_ids_timed, n_untimed):
     """Insert scans [0, n_untimed) untimed then the timed ones into a fresh reference map; -> seconds per timed scan."""
     from oracle.ref import RefMap
-    m = RefMap("bgk", dict(BGK), fast=True)
+    # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    m = RefMap("bgk", dict(BGK), fast=True, threads=os.cpu_count())
     cores = m.max_threads()
     for s in range(n_untimed):
         m.insert_pointcloud(pts[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
@@ -241,8 +242,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line the driver parses
+        # (NCCL's own chatter goes to stderr: claim_stdout() moved fd 1 there before anything was loaded)
         dist.init_process_group("nccl", device_id=dev)
 
     n = a.warmup + a.steps
@@ -372,6 +372,24 @@ def run_ours(a):
             pass
         ach_gbs = k_bytes / (k_ms * 1e-3) / 1e9
         ach_tf = k_flop / (k_ms * 1e-3) / 1e12
+        fp32_peak = float(fp32.value)
+        t_hbm_us = k_bytes / (hbm_peak * 1e9) * 1e6
+        t_fp32_us = k_flop / (fp32_peak * 1e12) * 1e6 if fp32_peak > 0 else 0.0
+        rl_hbm = {"kernel": "k_predict_bgk_flat (fused predict + Occupancy::update + prune)", "bound": "hbm",
+                  "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                  "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
+                  "kernel_share_of_step": k_ms / (1e3 * T / a.steps), "algorithmic_bytes": k_bytes,
+                  "t_min_us": t_hbm_us}
+        rl_fp32 = {"kernel": rl_hbm["kernel"], "bound": "fp32", "achieved": ach_tf, "peak": fp32_peak,
+                   "unit": "TFLOP/s", "frac": ach_tf / fp32_peak if fp32_peak > 0 else None, "traffic": traffic,
+                   "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": k_ms,
+                   "kernel_share_of_step": k_ms / (1e3 * T / a.steps), "algorithmic_flop": k_flop,
+                   "t_min_us": t_fp32_us,
+                   "peak_source": "la3dm_bench_fp32_peak: register-resident FMA loop, measured in this run"}
+        # the governing roofline is the one with the larger minimum time (t_min = max(B/BW, F/peak))
+        governing, other = (rl_fp32, rl_hbm) if t_fp32_us >= t_hbm_us else (rl_hbm, rl_fp32)
+        governing["note"] = ("governing bound = max(bytes / HBM peak, flops / fp32 peak); algorithmic units: 17 B per "
+                             "voxel visit + 16 B per training point + 64 B per test block, 24 flop per (leaf, point) pair")
         line = {
             "metric": METRIC, "value": U / T, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * T / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -389,15 +407,8 @@ def run_ours(a):
                     "api": "la3dm_insert_pointcloud (pinned host cloud) + la3dm_last_stats"},
             "gpu_launches": int(sum(st_d[s]["kernel_launches"] for s in timed)),
             "collectives_per_step": st_d[timed[0]]["collectives"],
-            "roofline": {"kernel": "k_predict_bgk_oct (fused predict + Occupancy::update + prune)", "bound": "hbm",
-                         "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
-                         "kernel_share_of_step": k_ms / (1e3 * T / a.steps), "algorithmic_bytes": k_bytes,
-                         "note": "the pair loop is fp32-pipe bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": float(fp32.value), "unit": "TFLOP/s",
-                              "frac": ach_tf / fp32.value if fp32.value > 0 else None,
-                              "flop_per_pair": FLOP_PER_PAIR,
-                              "peak_source": "la3dm_bench_fp32_peak: register-resident FMA loop, measured in this run"},
+            "roofline": governing,
+            "roofline_other": other,
             "clocks": clocks,
             "final_leaves": leaves_d,
         }

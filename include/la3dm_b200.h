@@ -138,7 +138,9 @@ int la3dm_insert_pointcloud(la3dm_map *map, const float *xyz, size_t n, size_t s
                             float ds_resolution, float free_res, float max_range);
 
 /* Same, with the scan already resident in device memory of the map's device (no host<->device copy of the cloud).
- * Work is enqueued on the map's stream; returns after the scan has been fully applied. */
+ * Work is enqueued on the map's OWN stream (la3dm_stream, created non-blocking); returns after the scan has been fully
+ * applied.  The cloud must be complete before the call: if another stream is still writing it (a kernel, an async
+ * copy), either synchronise that stream or call la3dm_stream_wait(map, that_stream) first. */
 int la3dm_insert_pointcloud_device(la3dm_map *map, const float *d_xyz, size_t n, size_t stride_bytes,
                                    const float origin[3], float ds_resolution, float free_res, float max_range);
 
@@ -214,6 +216,9 @@ int64_t la3dm_shard_rows(const la3dm_map *map);                  /* rows per ran
 int la3dm_shard_pack(la3dm_map *map, void *d_rows);              /* writes la3dm_shard_rows() rows          */
 int la3dm_shard_unpack(la3dm_map *map, const void *d_all_rows);  /* reads world * la3dm_shard_rows() rows   */
 void *la3dm_stream(la3dm_map *map);                              /* cudaStream_t the map enqueues on        */
+/* Orders the map's stream after everything enqueued so far on producer_stream (a cudaStream_t; NULL = the legacy
+ * default stream): event record + stream wait, no host synchronisation. */
+int la3dm_stream_wait(la3dm_map *map, void *producer_stream);
 
 /* ---- measurement helper -------------------------------------------------------------------------------------- */
 /* FP32 FMA throughput of `device` (TFLOP/s, 2 flop per FMA) from a register-resident FMA loop timed with CUDA

@@ -76,6 +76,7 @@ SYMBOLS = {
     "la3dm_shard_pack": (C.c_int, [_P, _P]),
     "la3dm_shard_unpack": (C.c_int, [_P, _P]),
     "la3dm_stream": (_P, [_P]),
+    "la3dm_stream_wait": (C.c_int, [_P, _P]),
     "la3dm_bench_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
 }
 

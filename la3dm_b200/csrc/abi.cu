@@ -262,12 +262,28 @@ int la3dm_get_bbox(la3dm_map *map, float lim_min[3], float lim_max[3]) {
 
 int la3dm_set_shard(la3dm_map *map, int rank, int world) {
     if (!map || world < 1 || rank < 0 || rank >= world) return LA3DM_ERR_INVALID;
+    // BGKLV predicts per voxel through its own block list (k_lv_blocks / k_lv_predict), which does not honour the shard
+    // and never fills the neighbour plan the exchange indexes: refuse instead of exchanging garbage
+    if (world > 1 && map->m.hp.method == LA3DM_BGKLV) {
+        map->m.last_error = "sharding is not implemented for BGKLV";
+        return LA3DM_ERR_UNSUPPORTED;
+    }
     map->m.shard_rank = rank;
     map->m.shard_world = world;
     return LA3DM_OK;
 }
 
 void *la3dm_stream(la3dm_map *map) { return map ? (void *) map->m.stream : nullptr; }
+
+int la3dm_stream_wait(la3dm_map *map, void *producer_stream) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] {
+        Map &m = map->m;
+        LA3DM_CUDA(cudaSetDevice(m.device));
+        LA3DM_CUDA(cudaEventRecord(m.ev_wait, (cudaStream_t) producer_stream));
+        LA3DM_CUDA(cudaStreamWaitEvent(m.stream, m.ev_wait, 0));
+    });
+}
 
 }  // extern "C"
 

@@ -122,6 +122,7 @@ Map::~Map() {
     if (ev1) cudaEventDestroy(ev1);
     if (ev_p0) cudaEventDestroy(ev_p0);
     if (ev_p1) cudaEventDestroy(ev_p1);
+    if (ev_wait) cudaEventDestroy(ev_wait);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -129,6 +130,9 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     if (method < LA3DM_BGK || method > LA3DM_GP) throw StatusError{LA3DM_ERR_INVALID, "unknown method"};
     if (p.block_depth < 1 || p.block_depth > kMaxDepth) throw StatusError{LA3DM_ERR_INVALID, "block_depth out of range"};
     if (!(p.resolution > 0) || !(p.ell > 0)) throw StatusError{LA3DM_ERR_INVALID, "resolution and ell must be > 0"};
+    // configurations the predict kernels do not cover are refused HERE, before any scan can touch the map
+    if (method == LA3DM_GP && p.block_depth > 4)
+        throw StatusError{LA3DM_ERR_UNSUPPORTED, "GPOctoMap: block_depth > 4 is not implemented"};
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -145,6 +149,7 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     LA3DM_CUDA(cudaEventCreate(&ev1));
     LA3DM_CUDA(cudaEventCreate(&ev_p0));
     LA3DM_CUDA(cudaEventCreate(&ev_p1));
+    LA3DM_CUDA(cudaEventCreateWithFlags(&ev_wait, cudaEventDisableTiming));
     const char *env = getenv("LA3DM_NO_GRAPH");
     use_graph = !(env && env[0] == '1');
 

@@ -23,7 +23,7 @@ struct Map {
     std::vector<float3> h_lut;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_wait = nullptr;
     int num_sms = 148;
     std::string last_error;
 

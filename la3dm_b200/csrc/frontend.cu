@@ -697,6 +697,9 @@ void Map::enqueue_scan(bool frontend_only) {
         else if (hp.method == LA3DM_BGKL) enqueue_predict_bgkl();
         else enqueue_predict();
     }
+    // a launch that was refused (bad configuration, missing function attribute) must surface as LA3DM_ERR_CUDA, not as
+    // a scan that silently did nothing
+    LA3DM_CUDA(cudaGetLastError());
 }
 
 // temp storage of the largest radix sort the scan issues

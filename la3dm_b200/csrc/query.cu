@@ -141,8 +141,13 @@ void Map::import_blocks(const int64_t *in_keys, const la3dm_node *in_nodes, size
     if (n == 0) return;
     if (!in_keys || !in_nodes) throw StatusError{LA3DM_ERR_INVALID, "import_blocks: null input"};
     if (n > 0x7FFFFFF0ull / (size_t) hp.nodes) throw StatusError{LA3DM_ERR_INVALID, "import_blocks: too many blocks"};
-    for (size_t i = 1; i < n; ++i)
-        if (in_keys[i] == in_keys[i - 1]) throw StatusError{LA3DM_ERR_INVALID, "import_blocks: duplicate block key"};
+    // keys strictly increasing (sorted, no duplicates anywhere) and inside the 3 x 20-bit key space; node states valid
+    for (size_t i = 0; i < n; ++i) {
+        if (in_keys[i] < 0 || in_keys[i] >= ((int64_t) 1 << 60)) throw StatusError{LA3DM_ERR_INVALID, "import_blocks: block key out of range"};
+        if (i && in_keys[i] <= in_keys[i - 1]) throw StatusError{LA3DM_ERR_INVALID, "import_blocks: block keys must be strictly increasing"};
+    }
+    for (size_t i = 0; i < n * (size_t) hp.nodes; ++i)
+        if (in_nodes[i].state > (uint8_t) hp.pruned_state) throw StatusError{LA3DM_ERR_INVALID, "import_blocks: invalid node state"};
     LA3DM_CUDA(cudaSetDevice(device));
     ensure_pool(n + caps.tests);
     const size_t total = n * (size_t) hp.nodes;
@@ -152,8 +157,13 @@ void Map::import_blocks(const int64_t *in_keys, const la3dm_node *in_nodes, size
     k_unpack_nodes<<<ceil_div((long long) total, kThreads), kThreads, 0, stream>>>(
         export_buf.as<la3dm_node>(), (unsigned int) n, d_params, pool.as<unsigned char>());
     n_blocks = (long long) n;
-    rebuild_hash();
-    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    try {
+        rebuild_hash();
+        LA3DM_CUDA(cudaStreamSynchronize(stream));
+    } catch (...) {
+        n_blocks = 0;          // a failed import leaves an empty map, not a half-filled one
+        throw;
+    }
 }
 
 void Map::save(const char *path) {

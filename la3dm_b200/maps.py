@@ -59,6 +59,9 @@ class _OctoMapBase:
         o = np.ascontiguousarray(origin, dtype=np.float32)
         if hasattr(cloud, "is_cuda") and cloud.is_cuda:
             assert cloud.dtype.itemsize == 4 and cloud.dim() == 2 and cloud.stride(1) == 1 and cloud.shape[1] >= 3
+            import torch
+            # the map enqueues on its own non-blocking stream: order it after whatever produced the tensor
+            self._check(self._lib.la3dm_stream_wait(self._h, torch.cuda.current_stream(cloud.device).cuda_stream))
             self._check(self._lib.la3dm_insert_pointcloud_device(
                 self._h, cloud.data_ptr(), cloud.shape[0], cloud.stride(0) * 4, o.ctypes.data, float(ds_resolution),
                 float(free_res), float(max_range)))
