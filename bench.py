@@ -15,8 +15,9 @@ Three measurements on our arm:
           read-back of the scan counters happen inside the timed region;
   cpu_baseline / --impl reference: the reference's own sources (oracle/_ref, "fast" flavour, all host threads).
 N > 1 (torchrun): every rank holds a replica of the map and runs the front-end redundantly, the test blocks of the scan
-are dealt over ranks inside the predict kernel and the updated block rows are exchanged with ONE NCCL all-gather per
-scan; the same scan is split over more GPUs => "scaling": "strong".
+are dealt over ranks inside the predict kernel, and each rank's predict kernel stores its updated nodes straight into
+every replica's pool through NVLink-mapped pointers (no pack / collective / unpack; LA3DM_EXCHANGE=nccl selects round 1's
+all-gather of packed rows for comparison); the same scan is split over more GPUs => "scaling": "strong".
 """
 import argparse
 import ctypes
@@ -58,6 +59,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-sample-scans", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reserve-blocks", type=int, default=4000000, help="N > 1: block slots allocated up front")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
     return a
@@ -256,10 +258,22 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_nccl_rows = os.environ.get("LA3DM_EXCHANGE", "peer") == "nccl"   # A/B: round 1's pack / all-gather / unpack
+
     def new_map():
         m = la3dm_b200.BGKOctoMap(device=local, **BGK)
-        if world > 1:
+        if world > 1 and use_nccl_rows:
             m.set_shard(rank, world)
+        elif world > 1:
+            from la3dm_b200 import sharding
+
+            def gather(obj):
+                lst = [None] * world
+                dist.all_gather_object(lst, obj)
+                return lst
+
+            m.reserve_blocks(a.reserve_blocks)       # the pool must not move while peers are attached
+            sharding.attach_peers(m, rank, world, gather)
         return m
 
     xbuf = {}
@@ -300,7 +314,7 @@ def run_ours(a):
                 m.insert_pointcloud(h_scans[s].numpy(), org[s], DS_RES, FREE_RES, MAX_RANGE)
             else:
                 m.insert_pointcloud(d_scans[s], org[s], DS_RES, FREE_RES, MAX_RANGE)
-            ncoll = exchange(m, ms_stream) if world > 1 else 0
+            ncoll = exchange(m, ms_stream) if (world > 1 and use_nccl_rows) else 0
             st = m.last_stats()                    # D2H read-back of the scan counters happened inside the call
             e1.record(ms_stream)
             e1.synchronize()
@@ -407,6 +421,8 @@ def run_ours(a):
                     "api": "la3dm_insert_pointcloud (pinned host cloud) + la3dm_last_stats"},
             "gpu_launches": int(sum(st_d[s]["kernel_launches"] for s in timed)),
             "collectives_per_step": st_d[timed[0]]["collectives"],
+            "exchange": (None if world == 1 else "nccl all-gather of packed block rows" if use_nccl_rows else
+                         "peer stores from inside the predict kernel (NVLink-mapped pools) + completion flags"),
             "roofline": governing,
             "roofline_other": other,
             "clocks": clocks,

@@ -220,6 +220,28 @@ void *la3dm_stream(la3dm_map *map);                              /* cudaStream_t
  * default stream): event record + stream wait, no host synchronisation. */
 int la3dm_stream_wait(la3dm_map *map, void *producer_stream);
 
+/* ---- multi-GPU, BGKOctoMap: replicas kept identical by peer stores from inside the predict kernel ------------------ */
+/* Every rank holds a replica and runs the front-end; rank r predicts the test blocks t % world == r and its predict
+ * kernel stores every updated node (and the state bytes of every block it changed) into ALL replicas' pools through
+ * peer-mapped pointers (NVLink), then flags the scan as complete in every peer's memory; la3dm_insert_pointcloud*
+ * returns once all peers have flagged it too.  No pack / collective / unpack, nothing for the caller to do per scan --
+ * but every rank MUST insert the same scans in the same order (the replicas, slot numbering included, are a function of
+ * the scans alone).  Set-up, once:
+ *   1. la3dm_reserve_blocks(map, n): room for n blocks up front -- the pool must not move while peers are attached
+ *      (an insert that would have to grow it fails with LA3DM_ERR_NOMEM);
+ *   2. same process (one thread per GPU): la3dm_peer_local() on every map; other processes: la3dm_peer_ipc_export(),
+ *      hand the two 64-byte handles to the peers by whatever transport the ranks share, la3dm_peer_ipc_open() there;
+ *   3. la3dm_peer_attach(map, world, rank, pool_bases, flags): arrays of `world` device pointers, entry [rank] ignored.
+ * world <= 8 (one NVSwitch domain). */
+#define LA3DM_IPC_HANDLE_BYTES 64
+int la3dm_reserve_blocks(la3dm_map *map, size_t blocks);
+int la3dm_peer_local(la3dm_map *map, void **pool_base, void **flags);
+int la3dm_peer_ipc_export(la3dm_map *map, void *handle_pool, void *handle_flags);
+int la3dm_peer_ipc_open(la3dm_map *map, const void *handle_pool, const void *handle_flags, void **pool_base,
+                        void **flags);
+int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bases, void *const *flags);
+int la3dm_peer_detach(la3dm_map *map);
+
 /* ---- measurement helper -------------------------------------------------------------------------------------- */
 /* FP32 FMA throughput of `device` (TFLOP/s, 2 flop per FMA) from a register-resident FMA loop timed with CUDA
  * events: the denominator for the fp32-pipe roofline of the predict kernel (SURVEY.md section 8d asks for it to be

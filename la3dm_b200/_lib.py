@@ -75,6 +75,12 @@ SYMBOLS = {
     "la3dm_shard_rows": (C.c_int64, [_P]),
     "la3dm_shard_pack": (C.c_int, [_P, _P]),
     "la3dm_shard_unpack": (C.c_int, [_P, _P]),
+    "la3dm_reserve_blocks": (C.c_int, [_P, C.c_size_t]),
+    "la3dm_peer_local": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "la3dm_peer_ipc_export": (C.c_int, [_P, _P, _P]),
+    "la3dm_peer_ipc_open": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P)]),
+    "la3dm_peer_attach": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "la3dm_peer_detach": (C.c_int, [_P]),
     "la3dm_stream": (_P, [_P]),
     "la3dm_stream_wait": (C.c_int, [_P, _P]),
     "la3dm_bench_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),

@@ -324,29 +324,119 @@ __global__ void k_test_place(const unsigned int *__restrict__ bits, unsigned int
 }
 
 // ---- persistent block map -----------------------------------------------------------------------------------------
-// One thread per test block: find or create its slot in the map, and look up the training ranges of its 7 neighbours
-// [self,+x,-x,+y,-y,+z,-z] (src/bgkoctomap/bgkblock.cpp:85-101) through the cell -> data block table.
-// This is the first kernel of the scan that touches the persistent map; every capacity check has been made by now.
-__global__ void k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs *__restrict__ A,
-                       const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
-                       const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask,
-                       long long *keys, NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list) {
+// Block key of test block t (dense cell id -> absolute block indices -> BlockHashKey, bgkblock.cpp:73-77)
+__device__ inline long long test_block_key(unsigned int id, const GridDesc *g, int &x, int &y, int &z) {
+    const int nz = g->n[2], ny = g->n[1];
+    z = (int) (id % (unsigned int) nz);
+    y = (int) ((id / (unsigned int) nz) % (unsigned int) ny);
+    x = (int) (id / ((unsigned int) nz * (unsigned int) ny));
+    return make_key(g->base[0] + x, g->base[1] + y, g->base[2] + z);
+}
+
+// One thread per test block: look its key up in the map (slot, or 0xFFFFFFFF for a block that does not exist yet) and
+// count the new blocks of the tile.  Read-only on the map.
+__global__ void __launch_bounds__(kThreads)
+k_plan_find(const unsigned int *__restrict__ test_id, const ScanCounters *__restrict__ c, const GridDesc *__restrict__ g,
+            const long long *__restrict__ hkeys, const int *__restrict__ hvals, size_t mask, NeighbourPlan *plan,
+            unsigned int *tile_sums) {
+    __shared__ unsigned int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c->overflow || t >= c->n_test_blocks) return;
-    const unsigned int id = test_id[t];
-    const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
-    const int z = (int) (id % (unsigned int) nz), y = (int) ((id / (unsigned int) nz) % (unsigned int) ny),
-              x = (int) (id / ((unsigned int) nz * (unsigned int) ny));
-    const long long key = make_key(g->base[0] + x, g->base[1] + y, g->base[2] + z);
-    NeighbourPlan pl;
-    int slot = hash_find(hkeys, hvals, mask, key);
-    pl.is_new = slot < 0 ? 1u : 0u;
-    if (slot < 0) {
-        slot = (int) (A->n_blocks + atomicAdd(&c->n_new_blocks, 1u));   // < pool_cap: the host keeps room for `tests`
-        keys[slot] = key;
-        hash_insert(hkeys, hvals, mask, key, slot);
+    bool is_new = false;
+    if (!c->overflow && t < c->n_test_blocks) {
+        int x, y, z;
+        const long long key = test_block_key(test_id[t], g, x, y, z);
+        const int slot = hash_find(hkeys, hvals, mask, key);
+        is_new = slot < 0;
+        plan[t].slot = (unsigned int) slot;
     }
-    pl.slot = (unsigned int) slot;
+    const unsigned int m = __ballot_sync(0xffffffffu, is_new);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, (unsigned int) __popc(m));
+    __syncthreads();
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = s_cnt;
+}
+
+// One thread per test block: create the blocks that do not exist yet, and look up the training ranges of the 7
+// neighbours [self,+x,-x,+y,-y,+z,-z] (src/bgkoctomap/bgkblock.cpp:85-101) through the cell -> data block table.
+// New blocks get their slots in TEST-BLOCK ORDER (n_blocks + rank among the new ones): the slot numbering -- hence the
+// whole pool -- is a function of the scans alone, identical on every replica of a multi-GPU run, which is what lets a
+// rank store its results straight into its peers' pools.  For BGKOctoMap the record of a new block is also written
+// here (default node everywhere, bgkoctree_node.h:34), by the whole warp, so that every replica holds it whoever
+// predicts the block.  This is the first kernel of the scan that writes to the persistent map; every capacity check
+// has been made by now.
+__global__ void __launch_bounds__(kThreads)
+k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs *__restrict__ A,
+       const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
+       const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask, long long *keys,
+       NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list, const unsigned int *__restrict__ tile_sums,
+       unsigned int n_tiles, int prescanned, unsigned char *pool, const DevParams *__restrict__ P, int init_records) {
+    __shared__ unsigned int smem[66];
+    if (c->overflow) return;
+    unsigned int prefix, total;
+    if (prescanned) { prefix = tile_sums[blockIdx.x]; total = tile_sums[n_tiles]; }
+    else block_tile_prefix(tile_sums, blockIdx.x, n_tiles, smem, prefix, total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) c->n_new_blocks = total;
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < c->n_test_blocks;
+    NeighbourPlan pl;
+    pl.slot = valid ? plan[t].slot : 0u;
+    pl.is_new = (valid && pl.slot == 0xFFFFFFFFu) ? 1u : 0u;
+    unsigned int cta_total;
+    const unsigned int rank = block_exclusive_scan(pl.is_new, smem, cta_total);
+    int x = 0, y = 0, z = 0;
+    long long key = 0;
+    if (valid) key = test_block_key(test_id[t], g, x, y, z);
+    if (pl.is_new) {
+        pl.slot = A->n_blocks + prefix + rank;                       // < pool_cap: the host keeps room for `tests`
+        keys[pl.slot] = key;
+        hash_insert(hkeys, hvals, mask, key, (int) pl.slot);
+    }
+    if (init_records) {
+        // Default records of this warp's new blocks, 16 bytes per lane and step.  Multi-GPU: the rank that will predict
+        // the block (t % world) writes the record into EVERY replica -- a peer may be ahead of us, and its results must
+        // not be overwritten by a default record that we write later; stores of one GPU to one peer arrive in order, so
+        // the owner's defaults land before the owner's results.
+        const PeerTable *PT = A->peers;
+        const int world = PT ? PT->world : 1, my_rank = PT ? PT->rank : 0;
+        const bool mine = (int) (t % (unsigned int) A->shard_world) == A->shard_rank || !PT;
+        unsigned int todo = __ballot_sync(0xffffffffu, pl.is_new != 0u && mine);
+        const int lane = threadIdx.x & 31;
+        const int nodes = P->nodes, st_off = P->st_off, words = P->rec_bytes >> 4;
+        const float da = P->def_a, db = P->def_b;
+        const unsigned int leaves = (unsigned int) (P->finest & 0xFF);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned int sl = __shfl_sync(0xffffffffu, pl.slot, src);
+            const size_t rec_off = (size_t) sl * (size_t) P->rec_bytes;
+            for (int w = lane; w < words; w += 32) {
+                uint4 v;
+                unsigned int *vw = reinterpret_cast<unsigned int *>(&v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int byte0 = 16 * w + 4 * q;
+                    unsigned int word;
+                    if (byte0 + 4 <= st_off) word = __float_as_uint(((byte0 >> 2) & 1) ? db : da);
+                    else {
+                        word = 0;
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) {
+                            const int n = byte0 + bb - st_off;
+                            const unsigned int by = n < nodes ? (unsigned int) LA3DM_UNKNOWN : (n == nodes ? leaves : 0u);
+                            word |= by << (8 * bb);
+                        }
+                    }
+                    vw[q] = word;
+                }
+                reinterpret_cast<uint4 *>(pool + rec_off)[w] = v;
+                for (int p = 0; p < world; ++p)
+                    if (p != my_rank) reinterpret_cast<uint4 *>(PT->pool[p] + rec_off)[w] = v;
+            }
+        }
+    }
+    if (!valid) return;
+    const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
     unsigned int tot = 0;
     const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
 #pragma unroll
@@ -477,12 +567,20 @@ void Map::enqueue_binning() {
     k_test_place<<<w_tiles, kThreads, 0, stream>>>(test_bits.as<unsigned int>(), n_words, d_cnt, tile_sums,
                                                    (unsigned int) w_tiles, prescanned, test_id.as<unsigned int>(),
                                                    caps.tests);
-    k_plan<<<ceil_div(caps.tests, kThreads), kThreads, 0, stream>>>(
+    // slots of the test blocks: lookup + count of the new ones, then creation in test-block order
+    const int p_tiles = ceil_div(caps.tests, kThreads);
+    const int p_prescanned = p_tiles > 1024 ? 1 : 0;
+    k_plan_find<<<p_tiles, kThreads, 0, stream>>>(test_id.as<unsigned int>(), d_cnt, d_grid, hkeys.as<long long>(),
+                                                  hvals.as<int>(), hash_cap - 1, plan.as<NeighbourPlan>(), tile_sums);
+    if (p_prescanned) { k_tiles_scan<<<1, 1024, 0, stream>>>(tile_sums, (unsigned int) p_tiles); ++launches; }
+    k_plan<<<p_tiles, kThreads, 0, stream>>>(
         test_id.as<unsigned int>(), d_cnt, d_args, d_grid, cell_db.as<unsigned int>(),
         hp.method == LA3DM_BGKL ? seg_start.as<unsigned int>() : db_start.as<unsigned int>(),
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
         hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr,
-        hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr);
+        hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr, tile_sums, (unsigned int) p_tiles,
+        p_prescanned, pool.as<unsigned char>(), d_params, hp.method == LA3DM_BGK ? 1 : 0);
+    ++launches;
     launches += 3;
 }
 

@@ -100,6 +100,15 @@ struct DevParams {
     float ax_off[3][8];
 };
 
+// Multi-GPU: every rank holds a replica of the map; the rank that predicts a test block stores the result straight into
+// the other replicas' pools over NVLink (peer-mapped pointers), from inside the predict kernel.
+constexpr int kMaxPeers = 8;
+struct PeerTable {
+    unsigned char *pool[kMaxPeers];          // pool base of every rank's replica, as mapped on THIS device ([rank]: own)
+    unsigned long long *flags[kMaxPeers];    // flags[r][q], in rank r's memory: last scan that rank q has pushed completely
+    int world, rank;
+};
+
 // Arguments of one insert_pointcloud call.  They live in device memory (copied from a pinned host mirror at the head
 // of the scan) so that every kernel of the scan has launch parameters that do not change from scan to scan -- which is
 // what lets the whole scan be replayed as one CUDA graph.
@@ -119,6 +128,8 @@ struct ScanArgs {
     const float *beam_tab;  // beam_tab[e] = fr + fr + ... (e fp32 additions): distance of beam sample e
     unsigned int beam_tab_n;
     unsigned int heavy_tot; // test blocks with more neighbourhood points than this are predicted first (kHeavyTot)
+    const PeerTable *peers; // attached replicas (nullptr: none)
+    unsigned long long scan_seq;   // sequence number of this scan (peer completion flags)
 };
 
 // per-scan block grid: restates get_blocks_in_bbox (src/bgkoctomap/bgkoctomap.cpp:486-495) as a Cartesian product of
@@ -155,7 +166,7 @@ struct Caps {
 
 enum : unsigned int {
     OVF_RAW = 1u, OVF_MEMBERS = 2u, OVF_CELLS = 4u, OVF_TESTS = 8u, OVF_EXTENT = 16u, OVF_POOL = 32u, OVF_VGCELLS = 64u,
-    OVF_GPSTORE = 128u, OVF_GPN = 256u, OVF_LVACTIVE = 512u
+    OVF_GPSTORE = 128u, OVF_GPN = 256u, OVF_LVACTIVE = 512u, OVF_PEER = 1024u
 };
 
 // counters the host reads back once per scan (pinned mirror)
@@ -183,7 +194,7 @@ struct ScanCounters {
     unsigned int lv_active;      // BGKLV: active voxels of the scan
     unsigned int work_next;      // dynamic work distribution of the predict kernel (units handed out so far)
     unsigned int n_heavy;        // test blocks with more than kHeavyTot training points in their ExtendedBlock
-    unsigned int pad2_;
+    unsigned int ctas_done;      // CTAs of the predict kernel that have pushed everything to the peers
     unsigned long long gp_store_needed;
 };
 

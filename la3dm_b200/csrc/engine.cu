@@ -117,6 +117,7 @@ Map::~Map() {
     if (d_cnt) cudaFree(d_cnt);
     if (h_cnt) cudaFreeHost(h_cnt);
     if (d_args) cudaFree(d_args);
+    if (d_peers) cudaFree(d_peers);
     if (h_args) cudaFreeHost(h_args);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -279,7 +280,8 @@ void Map::ensure_workspace() {
         moved |= sort_vals[i].reserve(n_sort * 4, stream);
     }
     moved |= run_start.reserve((std::max<size_t>(caps.points, caps.raw) + 2) * 4, stream);
-    moved |= tiles.reserve((n_sort / kTile + (size_t) caps.points / 256 + (size_t) caps.cells / 32 / 256 + 16) * 8, stream);
+    moved |= tiles.reserve((n_sort / kTile + (size_t) caps.points / 256 + (size_t) caps.cells / 32 / 256 +
+                            (size_t) caps.tests / 256 + 16) * 8, stream);
     moved |= long_list.reserve((size_t) 2 * (kMaxLongRuns + kMaxMidRuns) * 4, stream);
     moved |= long_flags.reserve((std::max<size_t>(caps.points, caps.raw) / 256 + 2) * 13, stream);
     moved |= hit_cnt.reserve((size_t) caps.points * 4, stream);
@@ -348,6 +350,9 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (attempt > 12) throw StatusError{LA3DM_ERR_NOMEM, "scan workspace did not settle"};
         if (n > caps.points) caps.points = grow_to((unsigned int) n, 4096);
         ensure_workspace();
+        if (peers_attached && (size_t) n_blocks + caps.tests > pool_cap)
+            throw StatusError{LA3DM_ERR_NOMEM, "the block pool would have to move while peers are attached: "
+                                               "la3dm_reserve_blocks() more before la3dm_peer_attach()"};
         ensure_pool((size_t) n_blocks + caps.tests);
         ensure_beam_table(fr);
 
@@ -362,6 +367,8 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.beam_tab = beam_tab.as<float>(); a.beam_tab_n = kBeamTab;
         static const unsigned int heavy_tot = getenv("LA3DM_HEAVY_TOT") ? (unsigned int) atoi(getenv("LA3DM_HEAVY_TOT")) : kHeavyTot;
         a.heavy_tot = heavy_tot;
+        a.peers = (peers_attached && !frontend_only) ? d_peers : nullptr;
+        a.scan_seq = scan_seq + 1;
 
         LA3DM_CUDA(cudaEventRecord(ev0, stream));
         LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));
@@ -402,6 +409,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         ++replays;
         ++call_replays;
         if (ovf & OVF_EXTENT) throw StatusError{LA3DM_ERR_EXTENT, "scan bounding box spans too many blocks"};
+        if (ovf & OVF_PEER) throw StatusError{LA3DM_ERR_CUDA, "timed out waiting for a peer replica to finish the scan"};
         if (ovf & OVF_VGCELLS) {   // only the bit count matters (radix-sort passes): next power of two
             unsigned int v = 1u << 20;
             while (v < h_cnt->vg_cells_needed && v < 0x80000000u) v <<= 1;
@@ -419,6 +427,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }
 
+    if (!frontend_only) ++scan_seq;
     // blocks after the scan = blocks before + blocks k_plan / k_lv_blocks created (no overflow on this path)
     n_blocks = frontend_only ? n_blocks : (long long) h_args->n_blocks + (long long) h_cnt->n_new_blocks;
     last_T = frontend_only ? 0 : h_cnt->n_test_blocks;
@@ -435,11 +444,6 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     stats.replays = call_replays;
     stats.graph_captures = call_captures;
     stats.grid_irregular = (int32_t) h_cnt->grid_irregular;
-#ifdef LA3DM_FLAT_STATS
-    fprintf(stderr, "flat stats: blocks %u chunks %u surv %u np %u iters %u in %u drains %u (long/mid run counters included)\n",
-            h_cnt->pad2_, h_cnt->n_long_runs[1], h_cnt->n_mid_runs[1], h_cnt->vg_cells_needed, h_cnt->n_long_runs[0],
-            h_cnt->reserved_, h_cnt->n_mid_runs[0]);
-#endif
     stats.h2d_bytes = h2d_bytes + (long long) sizeof(ScanArgs);   // h2d_bytes: the cloud, set by the host entry point
     stats.d2h_bytes = d2h_bytes;
     h2d_bytes = 0;

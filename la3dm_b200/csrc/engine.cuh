@@ -78,6 +78,13 @@ struct Map {
     int shard_rank = 0, shard_world = 1;
     unsigned int last_T = 0;        // test blocks of the last scan
 
+    // ---- peers: replicas on other GPUs kept identical by direct stores from the predict kernel (shard.cu)
+    PeerTable h_peers{};
+    PeerTable *d_peers = nullptr;
+    DevBuf peer_flags;              // [kMaxPeers] u64, written by the peers
+    bool peers_attached = false;
+    unsigned long long scan_seq = 0;
+
     // ---- leaf export scratch
     DevBuf leaf_cnt, leaf_off, leaf_out, export_buf, export_tmp, order_keys[2], order_vals[2], block_order;
 
@@ -106,6 +113,7 @@ struct Map {
     void enqueue_predict();
     void enqueue_gp();
     void enqueue_gp_sizes();
+    void enqueue_peer_wait();
     // export
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();

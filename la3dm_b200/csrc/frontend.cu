@@ -696,6 +696,7 @@ void Map::enqueue_scan(bool frontend_only) {
         if (hp.method == LA3DM_GP) enqueue_gp();
         else if (hp.method == LA3DM_BGKL) enqueue_predict_bgkl();
         else enqueue_predict();
+        if (hp.method == LA3DM_BGK) enqueue_peer_wait();
     }
     // a launch that was refused (bad configuration, missing function attribute) must surface as LA3DM_ERR_CUDA, not as
     // a scan that silently did nothing

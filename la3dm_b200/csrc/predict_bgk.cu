@@ -253,10 +253,21 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                    ScanCounters *cnt, const unsigned int *__restrict__ heavy_list) {
     __shared__ __align__(16) FlatSmem sm[kFlatWarps];
     __shared__ DevParams Ps;
+    __shared__ unsigned char *s_peer_pool[kMaxPeers];       // the other replicas' pools (multi-GPU), own rank left out
+    __shared__ int s_n_peers;
     if (threadIdx.x < sizeof(DevParams) / 4)
         reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    const PeerTable *PT = A->peers;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (PT)
+            for (int p = 0; p < PT->world; ++p)
+                if (p != PT->rank) s_peer_pool[n++] = PT->pool[p];
+        s_n_peers = n;
+    }
     __syncthreads();
     if (cnt->overflow) return;
+    const int n_peers = s_n_peers;
     const DevParams &P = Ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int full = 0xffffffffu, lt = (1u << lane) - 1u;
@@ -277,9 +288,6 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
 
     unsigned int visits = 0, updates = 0;
     unsigned long long pairs = 0;
-#ifdef LA3DM_FLAT_STATS
-    unsigned int dbg_it = 0, dbg_chunks = 0, dbg_drains = 0, dbg_surv = 0, dbg_in = 0, dbg_blocks = 0, dbg_np = 0;
-#endif
 
     // Work units come from one atomic counter: first the heavy blocks (more than heavy_tot neighbourhood points, listed
     // by k_plan), one per unit, then units of kUnit consecutive test blocks of this rank (t % world == rank), the heavy
@@ -310,7 +318,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             const unsigned int my_start = plw;
             unsigned int my_count = __shfl_down_sync(full, plw, 7);
             if (lane >= 7) my_count = 0u;
-            const unsigned int slot = __shfl_sync(full, plw, 14), is_new = __shfl_sync(full, plw, 15);
+            const unsigned int slot = __shfl_sync(full, plw, 14);
             unsigned int pre = my_count;                                  // inclusive prefix over lanes 0..6
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) {
@@ -321,26 +329,12 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             if (!heavy_unit && heavy_list && tot > heavy_tot) continue;   // done in the first phase
             pre -= my_count;                                              // exclusive
             const unsigned int delta = my_start - pre;                    // point gi of neighbour k sits at gi + delta_k
-#ifdef LA3DM_FLAT_STATS
-            ++dbg_blocks;
-#endif
-            unsigned char *rec = pool + (size_t) slot * (size_t) rec_bytes;
+            const size_t rec_off = (size_t) slot * (size_t) rec_bytes;
+            unsigned char *rec = pool + rec_off;
             float2 *gab = reinterpret_cast<float2 *>(rec);
             unsigned int *gst = reinterpret_cast<unsigned int *>(rec + st_off);
-            // ---- state bytes (a fresh Block: the default node everywhere, bgkoctree_node.h:34; its record is written now)
-            unsigned int stw = 0;
-            if (is_new) {
-                for (int n = lane; n < nodes; n += 32) gab[n] = make_float2(P.def_a, P.def_b);
-                if (lane < nst_words) {
-                    stw = 0x02020202u;                                    // LA3DM_UNKNOWN x 4
-                    const int b0 = 4 * lane;                              // bytes b0 .. b0 + 3 of the state area
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (b0 + b >= nodes)
-                            stw = (stw & ~(0xFFu << (8 * b))) | ((b0 + b == nodes ? (unsigned int) (P.finest & 0xFF) : 0u) << (8 * b));
-                    gst[lane] = stw;
-                }
-            } else if (lane < nst_words) stw = gst[lane];
+            // ---- state bytes (k_plan has written the default record of a block created this scan)
+            const unsigned int stw = lane < nst_words ? gst[lane] : 0u;
             const long long key = keys[slot];
             // ---- 32 points of the neighbourhood (ranges concatenated in ExtendedBlock order)
             auto fetch = [&](unsigned int base, float4 &z) -> bool {
@@ -366,9 +360,6 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             // evaluates `c` (<= 32) waiting pairs: kernel value by all lanes, segmented sums per leaf, accumulate
             auto drain = [&](unsigned int c) {
                 __syncwarp();
-#ifdef LA3DM_FLAT_STATS
-                ++dbg_drains;
-#endif
                 const unsigned int pos = (qh + (unsigned int) lane) & (kFlatQ - 1);
                 const bool e = (unsigned int) lane < c;
                 float vy = 0.f, vk = 0.f;
@@ -470,9 +461,6 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 // ---- the chunk's pairs, leaf-major: pair i = leaf i / ns, survivor i % ns; each lane walks i = lane,
                 // lane + 32, ... keeping (leaf, survivor) incrementally
                 const unsigned int np = (unsigned int) Lf * ns;
-#ifdef LA3DM_FLAT_STATS
-                ++dbg_chunks; dbg_surv += ns; dbg_np += np;
-#endif
                 const unsigned int q32 = 32u / ns, r32 = 32u - q32 * ns;
                 unsigned int lp = (unsigned int) lane / ns, pi = (unsigned int) lane - lp * ns;
 #pragma unroll 1
@@ -486,9 +474,6 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                     }
                     const bool in = d2 < 1.0f;                   // k <= 0 for d >= 1 (clamped upstream)
                     const unsigned int m = __ballot_sync(full, in);
-#ifdef LA3DM_FLAT_STATS
-                    ++dbg_it; dbg_in += __popc(m);
-#endif
                     if (m != 0u) {
                         if (in) {
                             const unsigned int pos = (qt + __popc(m & lt)) & (kFlatQ - 1);
@@ -526,6 +511,8 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                         ab.x += s.x;
                         ab.y += s.y - s.x;
                         gab[n] = ab;
+                        for (int p = 0; p < n_peers; ++p)             // the same node of the same slot in every replica
+                            reinterpret_cast<float2 *>(s_peer_pool[p] + rec_off)[n] = ab;
                         // get_var (bgkoctree_node.h:60) is below 1/4 for any (m_A, m_B) > 0: only evaluated if it can matter
                         unsigned int ns_ = LA3DM_UNKNOWN;
                         bool known = true;
@@ -558,7 +545,10 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
 #pragma unroll
                             for (int i = 1; i < 8; ++i) same = same && ((sst[off + 8 * g + i] & 7) == s0);
                             if (same) {
-                                gab[poff + g] = __ldcg(&gab[off + 8 * g]);    // parent := child 0 (classified is not copied)
+                                const float2 c0 = __ldcg(&gab[off + 8 * g]);  // parent := child 0 (classified is not copied)
+                                gab[poff + g] = c0;
+                                for (int p = 0; p < n_peers; ++p)
+                                    reinterpret_cast<float2 *>(s_peer_pool[p] + rec_off)[poff + g] = c0;
                                 sst[poff + g] = (sst[poff + g] & 0x80) | s0;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) sst[off + 8 * g + i] = (sst[off + 8 * g + i] & 0x80) | kStPRUNED;
@@ -573,7 +563,12 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 if (n_pruned_groups && lane == 0) sst[nodes] = (unsigned char) (Lf - 7 * n_pruned_groups);
                 __syncwarp();
             }
-            if (lane < nst_words) gst[lane] = S.st[lane];
+            if (lane < nst_words) {
+                const unsigned int w_ = S.st[lane];
+                gst[lane] = w_;
+                for (int p = 0; p < n_peers; ++p)
+                    reinterpret_cast<unsigned int *>(s_peer_pool[p] + rec_off + st_off)[lane] = w_;
+            }
         }
     }
 
@@ -589,13 +584,16 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
         atomicAdd(&cnt->updates, u64);
         atomicAdd(&cnt->pairs, pairs);
     }
-#ifdef LA3DM_FLAT_STATS
-    if (lane == 0) {
-        atomicAdd(&cnt->n_long_runs[0], dbg_it); atomicAdd(&cnt->n_long_runs[1], dbg_chunks);
-        atomicAdd(&cnt->n_mid_runs[0], dbg_drains); atomicAdd(&cnt->n_mid_runs[1], dbg_surv);
-        atomicAdd(&cnt->reserved_, dbg_in); atomicAdd(&cnt->pad2_, dbg_blocks); atomicAdd(&cnt->vg_cells_needed, dbg_np);
+    // ---- multi-GPU: when the last CTA has pushed its results, tell every peer that this rank is done with the scan
+    if (n_peers) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&cnt->ctas_done, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            for (int p = 0; p < PT->world; ++p)
+                if (p != PT->rank) *reinterpret_cast<volatile unsigned long long *>(PT->flags[p] + PT->rank) = A->scan_seq;
+        }
     }
-#endif
 }
 
 

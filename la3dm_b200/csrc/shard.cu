@@ -4,6 +4,8 @@
 // rank runs the front-end and the binning redundantly, so all ranks agree on the test-block list and the neighbour
 // plan.  After the scan each rank packs the records of ITS test blocks into fixed-size rows; the caller all-gathers
 // the rows over NCCL/NVLink and every rank scatters the peers' rows into its replica.
+#include <cstring>
+
 #include "engine.cuh"
 
 namespace la3dm_b200 {
@@ -28,7 +30,32 @@ __global__ void k_shard_copy(const NeighbourPlan *__restrict__ plan, const unsig
     else for (int i = lane; i < words; i += 32) rec[i] = row[i];
 }
 
+// Peer replicas: waits until every attached peer has flagged this scan as pushed (its predict kernel's last CTA writes
+// flags[rank] in our memory after a system-wide fence).  Bounded: a peer that never arrives raises OVF_PEER instead of
+// hanging the device.
+__global__ void k_peer_wait(const ScanArgs *__restrict__ A, ScanCounters *c, const unsigned long long *flags) {
+    const PeerTable *PT = A->peers;
+    if (!PT || c->overflow) return;
+    const int p = threadIdx.x;
+    if (p >= PT->world || p == PT->rank) return;
+    const volatile unsigned long long *f = flags + p;
+    const unsigned long long want = A->scan_seq;
+    const long long t0 = clock64();
+    while (*f < want) {
+        if (clock64() - t0 > 20000000000ll) { atomicOr(&c->overflow, OVF_PEER); break; }   // ~10 s
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 }  // namespace
+
+void Map::enqueue_peer_wait() {
+    if (!peers_attached) return;
+    k_peer_wait<<<1, 32, 0, stream>>>(d_args, d_cnt, peer_flags.as<unsigned long long>());
+    ++launches;
+}
+
 }  // namespace la3dm_b200
 
 using la3dm_b200::Map;
@@ -58,6 +85,109 @@ static int shard_copy(la3dm_map *map, void *rows, int pack) {
         m.last_error = "shard copy kernel launch failed";
         return LA3DM_ERR_CUDA;
     }
+    return LA3DM_OK;
+}
+
+// ---- peer replicas ----------------------------------------------------------------------------------------------------
+static int peer_fail(la3dm_map *map, const char *what, cudaError_t e) {
+    map->m.last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return LA3DM_ERR_CUDA;
+}
+
+static int ensure_peer_buffers(la3dm_map *map) {
+    Map &m = map->m;
+    if (cudaSetDevice(m.device) != cudaSuccess) return LA3DM_ERR_CUDA;
+    if (!m.peer_flags.p) {
+        try { m.peer_flags.reserve(la3dm_b200::kMaxPeers * sizeof(unsigned long long), m.stream); }
+        catch (...) { return LA3DM_ERR_NOMEM; }
+        cudaMemsetAsync(m.peer_flags.p, 0, m.peer_flags.cap, m.stream);
+        cudaStreamSynchronize(m.stream);
+    }
+    if (!m.d_peers && cudaMalloc(&m.d_peers, sizeof(la3dm_b200::PeerTable)) != cudaSuccess) return LA3DM_ERR_NOMEM;
+    return LA3DM_OK;
+}
+
+int la3dm_reserve_blocks(la3dm_map *map, size_t blocks) {
+    if (!map) return LA3DM_ERR_INVALID;
+    if (map->m.peers_attached) { map->m.last_error = "reserve_blocks: detach the peers first"; return LA3DM_ERR_INVALID; }
+    try {
+        cudaSetDevice(map->m.device);
+        map->m.ensure_pool(blocks);
+        cudaStreamSynchronize(map->m.stream);
+    } catch (const la3dm_b200::CudaError &e) { return peer_fail(map, "reserve_blocks", e.code); }
+    catch (...) { return LA3DM_ERR_NOMEM; }
+    return LA3DM_OK;
+}
+
+int la3dm_peer_local(la3dm_map *map, void **pool_base, void **flags) {
+    if (!map || !pool_base || !flags) return LA3DM_ERR_INVALID;
+    const int rc = ensure_peer_buffers(map);
+    if (rc != LA3DM_OK) return rc;
+    *pool_base = map->m.pool.p;
+    *flags = map->m.peer_flags.p;
+    return LA3DM_OK;
+}
+
+int la3dm_peer_ipc_export(la3dm_map *map, void *handle_pool, void *handle_flags) {
+    if (!map || !handle_pool || !handle_flags) return LA3DM_ERR_INVALID;
+    const int rc = ensure_peer_buffers(map);
+    if (rc != LA3DM_OK) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == LA3DM_IPC_HANDLE_BYTES, "handle size");
+    cudaError_t e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle_pool), map->m.pool.p);
+    if (e != cudaSuccess) return peer_fail(map, "cudaIpcGetMemHandle(pool)", e);
+    e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle_flags), map->m.peer_flags.p);
+    if (e != cudaSuccess) return peer_fail(map, "cudaIpcGetMemHandle(flags)", e);
+    return LA3DM_OK;
+}
+
+int la3dm_peer_ipc_open(la3dm_map *map, const void *handle_pool, const void *handle_flags, void **pool_base, void **flags) {
+    if (!map || !handle_pool || !handle_flags || !pool_base || !flags) return LA3DM_ERR_INVALID;
+    if (cudaSetDevice(map->m.device) != cudaSuccess) return LA3DM_ERR_CUDA;
+    cudaIpcMemHandle_t hp_, hf_;
+    memcpy(&hp_, handle_pool, sizeof(hp_));
+    memcpy(&hf_, handle_flags, sizeof(hf_));
+    cudaError_t e = cudaIpcOpenMemHandle(pool_base, hp_, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return peer_fail(map, "cudaIpcOpenMemHandle(pool)", e);
+    e = cudaIpcOpenMemHandle(flags, hf_, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return peer_fail(map, "cudaIpcOpenMemHandle(flags)", e);
+    return LA3DM_OK;
+}
+
+int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bases, void *const *flags) {
+    if (!map || world < 2 || world > la3dm_b200::kMaxPeers || rank < 0 || rank >= world || !pool_bases || !flags)
+        return LA3DM_ERR_INVALID;
+    Map &m = map->m;
+    if (m.hp.method != LA3DM_BGK || m.hp.depth > 3) {
+        m.last_error = "peer replicas are implemented for BGKOctoMap with block_depth <= 3";
+        return LA3DM_ERR_UNSUPPORTED;
+    }
+    const int rc = ensure_peer_buffers(map);
+    if (rc != LA3DM_OK) return rc;
+    la3dm_b200::PeerTable &t = m.h_peers;
+    memset(&t, 0, sizeof(t));
+    t.world = world; t.rank = rank;
+    for (int p = 0; p < world; ++p) {
+        if (p != rank && (!pool_bases[p] || !flags[p])) return LA3DM_ERR_INVALID;
+        t.pool[p] = p == rank ? m.pool.as<unsigned char>() : static_cast<unsigned char *>(pool_bases[p]);
+        t.flags[p] = p == rank ? m.peer_flags.as<unsigned long long>() : static_cast<unsigned long long *>(flags[p]);
+    }
+    cudaStreamSynchronize(m.stream);
+    cudaError_t e = cudaMemcpy(m.d_peers, &t, sizeof(t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return peer_fail(map, "peer table upload", e);
+    m.shard_rank = rank;
+    m.shard_world = world;
+    m.peers_attached = true;
+    m.invalidate_graph();
+    return LA3DM_OK;
+}
+
+int la3dm_peer_detach(la3dm_map *map) {
+    if (!map) return LA3DM_ERR_INVALID;
+    map->m.peers_attached = false;
+    map->m.shard_rank = 0;
+    map->m.shard_world = 1;
+    map->m.invalidate_graph();
     return LA3DM_OK;
 }
 

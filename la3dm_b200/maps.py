@@ -206,6 +206,37 @@ class _OctoMapBase:
     def stream(self):
         return int(self._lib.la3dm_stream(self._h) or 0)
 
+    # ---- peer replicas (BGKOctoMap): results stored straight into the other replicas' pools by the predict kernel
+    def reserve_blocks(self, n):
+        self._check(self._lib.la3dm_reserve_blocks(self._h, int(n)))
+
+    def peer_local(self):
+        """(pool_base, flags) device pointers of this replica, for peers living in the same process."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.la3dm_peer_local(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def peer_ipc_export(self):
+        """Two 64-byte CUDA IPC handles (pool, flags) as bytes, for peers in other processes."""
+        hp, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._check(self._lib.la3dm_peer_ipc_export(self._h, hp, hf))
+        return hp.raw, hf.raw
+
+    def peer_ipc_open(self, handle_pool, handle_flags):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.la3dm_peer_ipc_open(self._h, C.create_string_buffer(handle_pool, 64),
+                                                  C.create_string_buffer(handle_flags, 64), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def peer_attach(self, world, rank, pool_bases, flags):
+        P = C.c_void_p * world
+        self._check(self._lib.la3dm_peer_attach(self._h, int(world), int(rank),
+                                                P(*[C.c_void_p(int(v)) for v in pool_bases]),
+                                                P(*[C.c_void_p(int(v)) for v in flags])))
+
+    def peer_detach(self):
+        self._check(self._lib.la3dm_peer_detach(self._h))
+
 
 class BGKOctoMap(_OctoMapBase):
     METHOD = "bgk"

@@ -105,3 +105,60 @@ def test_index_maps():
 def test_exchange_world2_gloo_odd_and_empty():
     _run(1001, 29631)     # ragged: the last row of rank 1 is padding
     _run(0, 29632)        # a scan without test blocks issues no collective
+
+
+class FakePeerMap:
+    """Stands in for la3dm_b200.BGKOctoMap in attach_peers(): handles are (rank-tagged) byte strings, 'opening' one
+    returns pointers derived from the tag, so the test can check who attached what."""
+
+    def __init__(self, rank):
+        self.rank, self.attached = rank, None
+
+    def peer_ipc_export(self):
+        return (b"P%03d" % self.rank).ljust(64, b"\0"), (b"F%03d" % self.rank).ljust(64, b"\0")
+
+    def peer_ipc_open(self, hp, hf):
+        assert hp[:1] == b"P" and hf[:1] == b"F" and hp[1:4] == hf[1:4]
+        q = int(hp[1:4])
+        assert q != self.rank                       # a rank never opens its own handle (cudaIpcOpenMemHandle would fail)
+        return 0x1000 + q, 0x2000 + q
+
+    def peer_attach(self, world, rank, pools, flags):
+        self.attached = (world, rank, list(pools), list(flags))
+
+
+def _peer_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from la3dm_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def gather(obj):
+        lst = [None] * world
+        dist.all_gather_object(lst, obj)
+        return lst
+
+    m = FakePeerMap(rank)
+    sharding.attach_peers(m, rank, world, gather)
+    w, r, pools, flags = m.attached
+    ok = w == world and r == rank and all((pools[q], flags[q]) == ((0, 0) if q == rank else (0x1000 + q, 0x2000 + q))
+                                          for q in range(world))
+    res = gather(bool(ok))
+    if rank == 0:
+        out.put(all(res))
+    dist.destroy_process_group()
+
+
+def test_attach_peers_world2_gloo():
+    """la3dm_b200.sharding.attach_peers: every rank exports its two IPC handles, ONE all_gather_object moves them, every
+    rank opens the others' (never its own) and attaches pointer tables indexed by rank."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, 29633, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
