@@ -144,6 +144,17 @@ int la3dm_insert_pointcloud(la3dm_map *map, const float *xyz, size_t n, size_t s
 int la3dm_insert_pointcloud_device(la3dm_map *map, const float *d_xyz, size_t n, size_t stride_bytes,
                                    const float origin[3], float ds_resolution, float free_res, float max_range);
 
+/* Replaces  void insert_training_data(const GPPointCloud &xy)  (include/bgkoctomap/bgkoctomap.h:86,
+ * src/bgkoctomap/bgkoctomap.cpp:82-212; include/gpoctomap/gpoctomap.h, src/gpoctomap/gpoctomap.cpp:71-203): the same
+ * update WITHOUT the front-end -- the caller's pre-labelled points are the training set.  xyzy: n records of
+ * stride_bytes (>= 16), x y z label as float32.  As upstream, BGKOctoMap applies Occupancy::update to every leaf of every
+ * test block here (bgkoctomap.cpp:179 has no `kbar > 0` guard: untouched voxels become `classified`).  Upstream
+ * dereferences a null Block* when a test block does not exist yet (:155-160, `block` stays nullptr after emplace); here
+ * the block is created, like insert_pointcloud does.  BGKOctoMap and GPOctoMap only (the -L/-LV classes have no such
+ * member): LA3DM_ERR_UNSUPPORTED otherwise. */
+int la3dm_insert_training_data(la3dm_map *map, const float *xyzy, size_t n, size_t stride_bytes);
+int la3dm_insert_training_data_device(la3dm_map *map, const float *d_xyzy, size_t n, size_t stride_bytes);
+
 /* Front-end only: get_training_data() (src/bgkoctomap/bgkoctomap.cpp:383-417).  Runs the GPU front-end on a HOST
  * cloud and returns the training set; does not touch the map.  Call with out == NULL to get the count.
  * out: 7 floats per entry (x0 y0 z0 x1 y1 z1 label); for BGK/GP x1..z1 repeat x0..z0. */

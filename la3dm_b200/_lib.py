@@ -53,6 +53,8 @@ SYMBOLS = {
     "la3dm_insert_pointcloud": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float, C.c_float]),
     "la3dm_insert_pointcloud_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float,
                                                  C.c_float]),
+    "la3dm_insert_training_data": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
+    "la3dm_insert_training_data_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
     "la3dm_training_data": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float, C.c_float, _P,
                                       C.c_size_t, C.POINTER(C.c_size_t)]),
     "la3dm_training_rays": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_size_t]),

@@ -86,7 +86,7 @@ int la3dm_insert_pointcloud_device(la3dm_map *map, const float *d_xyz, size_t n,
                                    const float origin[3], float ds_resolution, float free_res, float max_range) {
     if (!map || !origin) return LA3DM_ERR_INVALID;
     return guarded(map, [&] {
-        map->m.insert_device(d_xyz, n, stride_bytes, origin, ds_resolution, free_res, max_range, false);
+        map->m.insert_device(d_xyz, n, stride_bytes, origin, ds_resolution, free_res, max_range, 0);
     });
 }
 
@@ -100,7 +100,29 @@ int la3dm_insert_pointcloud(la3dm_map *map, const float *xyz, size_t n, size_t s
         m.cloud.reserve(n * stride_bytes + 16, m.stream);
         if (n) LA3DM_CUDA(cudaMemcpyAsync(m.cloud.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, m.stream));
         m.h2d_bytes = (long long) (n * stride_bytes);
-        m.insert_device(m.cloud.as<float>(), n, stride_bytes, origin, ds_resolution, free_res, max_range, false);
+        m.insert_device(m.cloud.as<float>(), n, stride_bytes, origin, ds_resolution, free_res, max_range, 0);
+    });
+}
+
+int la3dm_insert_training_data(la3dm_map *map, const float *xyzy, size_t n, size_t stride_bytes) {
+    if (!map || (n && !xyzy)) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] {
+        Map &m = map->m;
+        LA3DM_CUDA(cudaSetDevice(m.device));
+        if (stride_bytes < 16 || stride_bytes % 4) throw la3dm_b200::StatusError{LA3DM_ERR_INVALID, "bad stride_bytes"};
+        m.cloud.reserve(n * stride_bytes + 16, m.stream);
+        if (n) LA3DM_CUDA(cudaMemcpyAsync(m.cloud.p, xyzy, n * stride_bytes, cudaMemcpyHostToDevice, m.stream));
+        m.h2d_bytes = (long long) (n * stride_bytes);
+        const float o[3] = {0.f, 0.f, 0.f};
+        m.insert_device(m.cloud.as<float>(), n, stride_bytes, o, -1.f, 1.f, -1.f, 2);
+    });
+}
+
+int la3dm_insert_training_data_device(la3dm_map *map, const float *d_xyzy, size_t n, size_t stride_bytes) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] {
+        const float o[3] = {0.f, 0.f, 0.f};
+        map->m.insert_device(d_xyzy, n, stride_bytes, o, -1.f, 1.f, -1.f, 2);
     });
 }
 
@@ -114,7 +136,7 @@ int la3dm_training_data(la3dm_map *map, const float *xyz, size_t n, size_t strid
         if (stride_bytes < 12 || stride_bytes % 4) throw la3dm_b200::StatusError{LA3DM_ERR_INVALID, "bad stride_bytes"};
         m.cloud.reserve(n * stride_bytes + 16, m.stream);
         if (n) LA3DM_CUDA(cudaMemcpyAsync(m.cloud.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, m.stream));
-        m.insert_device(m.cloud.as<float>(), n, stride_bytes, origin, ds_resolution, free_res, max_range, true);
+        m.insert_device(m.cloud.as<float>(), n, stride_bytes, origin, ds_resolution, free_res, max_range, 1);
         const size_t nt = (size_t) m.stats.n_train;
         if (n_out) *n_out = nt;
         if (!out || nt == 0) return;

@@ -482,11 +482,13 @@ inline int bits_for(unsigned int n) {
 }  // namespace
 
 // capacity for `blocks` blocks in the pool and a hash table at <= 50 % load (host side, between scans)
-void Map::ensure_pool(size_t blocks) {
+void Map::ensure_pool(size_t blocks, bool exact) {
     if (blocks > pool_cap) {
-        // grow-only, doubling (a move copies the pool and invalidates the captured graph); first allocation ~1 GB
+        // grow-only (a move copies the pool and invalidates the captured graph); first allocation ~1 GB; doubling while
+        // the pool is small, +25 % once it holds tens of GB (the copy needs old and new side by side)
         const size_t first = ((size_t) 1 << 30) / (size_t) hp.rec_bytes;
-        const size_t want = std::max(2 * blocks + 1024, first);
+        const size_t big = ((size_t) 16 << 30) / (size_t) hp.rec_bytes;
+        const size_t want = exact ? blocks : std::max((blocks > big ? blocks + blocks / 4 : 2 * blocks) + 1024, first);
         keys.grow_keep(want * sizeof(long long), stream);
         pool.grow_keep(want * (size_t) hp.rec_bytes, stream);
         pool_cap = want;

@@ -122,6 +122,7 @@ struct ScanArgs {
     float max_range;
     float free_label;       // 0 (BGK) / -1 (GP)
     int frontend_only;
+    int training_data;      // 1: xyz holds pre-labelled points (x y z label); no front-end, no kbar guard (insert_training_data)
     int shard_rank, shard_world;
     unsigned int n_blocks;  // blocks in the map before this scan
     unsigned int pool_cap;  // block slots allocated

@@ -331,12 +331,17 @@ void Map::ensure_workspace() {
 }
 
 void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
-                        float max_range, bool frontend_only) {
-    if (stride_bytes < 12 || stride_bytes % 4 != 0) throw StatusError{LA3DM_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 12"};
+                        float max_range, int mode) {
+    const bool frontend_only = mode == 1, training = mode == 2;
+    if (stride_bytes < (training ? 16u : 12u) || stride_bytes % 4 != 0)
+        throw StatusError{LA3DM_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 12 (16 for labelled points)"};
+    if (training && hp.method != LA3DM_BGK && hp.method != LA3DM_GP)
+        throw StatusError{LA3DM_ERR_UNSUPPORTED, "insert_training_data exists for BGKOctoMap and GPOctoMap only"};
     if (n > 0x7FFFFFF0ull) throw StatusError{LA3DM_ERR_INVALID, "too many points"};
     if (n > 0 && !d_xyz) throw StatusError{LA3DM_ERR_INVALID, "null cloud"};
-    if (!(fr > 0)) throw StatusError{LA3DM_ERR_INVALID, "free_res must be > 0"};
-    if (ds == 0) throw StatusError{LA3DM_ERR_INVALID, "ds_resolution must not be 0"};
+    if (!training && !(fr > 0)) throw StatusError{LA3DM_ERR_INVALID, "free_res must be > 0"};
+    if (!training && ds == 0) throw StatusError{LA3DM_ERR_INVALID, "ds_resolution must not be 0"};
+    if (training) { ds = -1.f; fr = 1.f; }
     // BGKLV clamps the downsampling resolution to the map resolution (src/bgklvoctomap/bgklvoctomap.cpp:102-104)
     if (hp.method == LA3DM_BGKLV && ds > hp.resolution) ds = hp.resolution;
     LA3DM_CUDA(cudaSetDevice(device));
@@ -362,6 +367,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.ds = ds; a.inv_ds = 1.0f / ds; a.fr = fr; a.max_range = max_range;
         a.free_label = hp.method == LA3DM_GP ? -1.0f : 0.0f;   // src/gpoctomap/gpoctomap.cpp:399
         a.frontend_only = frontend_only ? 1 : 0;
+        a.training_data = training ? 1 : 0;
         a.shard_rank = shard_rank; a.shard_world = shard_world;
         a.n_blocks = (unsigned int) n_blocks; a.pool_cap = (unsigned int) pool_cap;
         a.beam_tab = beam_tab.as<float>(); a.beam_tab_n = kBeamTab;
@@ -373,12 +379,12 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         LA3DM_CUDA(cudaEventRecord(ev0, stream));
         LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));
         if (use_graph) {
-            if (!graph_exec || !(graph_caps == caps) || graph_frontend_only != (int) frontend_only) {
+            if (!graph_exec || !(graph_caps == caps) || graph_mode != mode) {
                 invalidate_graph();
                 cudaGraph_t g = nullptr;
                 LA3DM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
                 try {
-                    enqueue_scan(frontend_only);
+                    enqueue_scan(mode);
                 } catch (...) {
                     cudaStreamEndCapture(stream, &g);
                     if (g) cudaGraphDestroy(g);
@@ -389,14 +395,14 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
                 cudaGraphDestroy(g);
                 LA3DM_CUDA(e);
                 graph_caps = caps;
-                graph_frontend_only = (int) frontend_only;
+                graph_mode = mode;
                 graph_launches = launches;
                 ++call_captures;
             }
             LA3DM_CUDA(cudaGraphLaunch(graph_exec, stream));
             launches = graph_launches;
         } else {
-            enqueue_scan(frontend_only);
+            enqueue_scan(mode);
         }
         LA3DM_CUDA(cudaEventRecord(ev1, stream));
         // the one synchronisation of the scan: counters (and overflow bits) back to the host

@@ -69,7 +69,7 @@ struct Map {
     // ---- whole-scan CUDA graph (re-captured when capacities or buffers change)
     cudaGraphExec_t graph_exec = nullptr;
     Caps graph_caps{};
-    int graph_frontend_only = -1;
+    int graph_mode = -1;
     int graph_launches = 0;
     bool use_graph = true;
     int replays = 0;                // scans re-run after a capacity overflow (lifetime counter)
@@ -92,15 +92,17 @@ struct Map {
     ~Map();
 
     void init(int method, const la3dm_params &p, int device);
-    void ensure_pool(size_t blocks);
+    void ensure_pool(size_t blocks, bool exact = false);
     void ensure_workspace();
     void ensure_beam_table(float fr);
     void invalidate_graph();
     void record_event(cudaEvent_t ev);   // inside or outside of a stream capture
+    // mode: 0 insert_pointcloud, 1 front-end only (get_training_data), 2 insert_training_data (d_xyz = x y z label)
     void insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
-                       float max_range, bool frontend_only);
+                       float max_range, int mode);
     // the scan, enqueued on `stream` without host synchronisation (graph-capturable)
-    void enqueue_scan(bool frontend_only);
+    void enqueue_scan(int mode);
+    void enqueue_training_data();
     void enqueue_frontend_bgk();
     void enqueue_frontend_bgkl();
     void enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int *sorted_vals);

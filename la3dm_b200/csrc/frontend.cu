@@ -604,6 +604,31 @@ k_hit_fill(const float4 *__restrict__ hits, ScanCounters *c, const ScanArgs *__r
     block_minmax_box(any_h, hmn, hmx, mm_xy, s_mm);
 }
 
+// insert_training_data (src/bgkoctomap/bgkoctomap.cpp:82-94): the caller's labelled points ARE the training set.  Copies
+// them to xy, accumulates the bounding box (bbox(), :464-484) and sets the counters the binning stage reads.
+__global__ void k_td_load(const ScanArgs *__restrict__ A, ScanCounters *c, float4 *xy, unsigned int train_cap,
+                          unsigned int *mm_xy) {
+    const unsigned int n = A->n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c->n_hits = 0; c->n_frees = 0; c->n_train = n;
+        if (n > train_cap) atomicOr(&c->overflow, OVF_RAW);
+    }
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-mn[0], -mn[0], -mn[0]};
+    bool any = false;
+    if (n <= train_cap)
+        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const float *p = A->xyz + (size_t) i * A->stride_f;
+            const float4 v = make_float4(p[0], p[1], p[2], p[3]);
+            xy[i] = v;
+            mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+            any = true;
+        }
+    __shared__ unsigned int s_mm[6];
+    block_minmax_box(any, mn, mx, mm_xy, s_mm);
+}
+
 inline int bits_for(unsigned int n) {   // radix-sort end bit for keys < n
     int b = 1;
     while (b < 32 && (1ull << b) < (unsigned long long) n) ++b;
@@ -682,11 +707,19 @@ void Map::enqueue_frontend_bgk() {
 }
 
 // The whole scan, stream-ordered, no host synchronisation (this is what the CUDA graph captures).
-void Map::enqueue_scan(bool frontend_only) {
+void Map::enqueue_training_data() {
+    const int grid = std::max(1, std::min(ceil_div(caps.train, kThreads), num_sms * 8));
+    k_td_load<<<grid, kThreads, 0, stream>>>(d_args, d_cnt, xy.as<float4>(), caps.train, d_mm + 12);
+    ++launches;
+}
+
+void Map::enqueue_scan(int mode) {
+    const bool frontend_only = mode == 1;
     launches = 0;
     k_scan_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm);
     ++launches;
-    if (hp.method == LA3DM_BGKL) enqueue_frontend_bgkl();
+    if (mode == 2) enqueue_training_data();
+    else if (hp.method == LA3DM_BGKL) enqueue_frontend_bgkl();
     else if (hp.method == LA3DM_BGKLV) enqueue_frontend_lv();
     else enqueue_frontend_bgk();
     if (!frontend_only && hp.method == LA3DM_BGKLV) {

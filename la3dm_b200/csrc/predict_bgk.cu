@@ -282,6 +282,8 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     const float inv_ell = 1.0f / ell;
     const float occ_t = P.occupied_thresh, free_t = P.free_thresh, var_t = P.var_thresh;
     const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
+    // insert_training_data has no `kbar > 0` guard (bgkoctomap.cpp:179): every leaf of a test block is updated
+    const bool no_guard = A->training_data != 0;
     // every leaf centre lies within (block_size - resolution) / 2 of the block centre (conservative, in units of ell)
     const float reach = 0.5f * (bs - P.resolution) * 1.001f / ell;
     const float cull2 = 1.0f + 1e-4f;
@@ -400,7 +402,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 if (keep) S.pt[ns + __popc(kept & lt)] = z;
                 ns += __popc(kept);
                 const bool last = base + 32 >= tot;
-                if (ns == 0 || (!last && ns <= (unsigned int) (kFlatPts - 32))) continue;
+                if ((ns == 0 && !(no_guard && last && Lf < 0)) || (!last && ns <= (unsigned int) (kFlatPts - 32))) continue;
                 // ---- list the block's leaves once: centre / ell and node index; zero their accumulators
                 if (Lf < 0) {
                     if (kD3) {
@@ -460,6 +462,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 __syncwarp();
                 // ---- the chunk's pairs, leaf-major: pair i = leaf i / ns, survivor i % ns; each lane walks i = lane,
                 // lane + 32, ... keeping (leaf, survivor) incrementally
+                if (ns == 0) continue;                            // (no_guard: the leaves were listed for the update only)
                 const unsigned int np = (unsigned int) Lf * ns;
                 const unsigned int q32 = 32u / ns, r32 = 32u - q32 * ns;
                 unsigned int lp = (unsigned int) lane / ns, pi = (unsigned int) lane - lp * ns;
@@ -505,7 +508,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 const int lq = lp0 + lane;
                 if (lq < Lf) {
                     const float2 s = S.acc[lq];
-                    if (s.y > 0.0f) {
+                    if (s.y > 0.0f || no_guard) {
                         const int n = __float_as_int(S.leaf[lq].w);
                         float2 ab = gab[n];
                         ab.x += s.x;

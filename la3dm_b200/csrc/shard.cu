@@ -113,7 +113,7 @@ int la3dm_reserve_blocks(la3dm_map *map, size_t blocks) {
     if (map->m.peers_attached) { map->m.last_error = "reserve_blocks: detach the peers first"; return LA3DM_ERR_INVALID; }
     try {
         cudaSetDevice(map->m.device);
-        map->m.ensure_pool(blocks);
+        map->m.ensure_pool(blocks, true);
         cudaStreamSynchronize(map->m.stream);
     } catch (const la3dm_b200::CudaError &e) { return peer_fail(map, "reserve_blocks", e.code); }
     catch (...) { return LA3DM_ERR_NOMEM; }

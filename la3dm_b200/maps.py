@@ -72,6 +72,11 @@ class _OctoMapBase:
         self._check(self._lib.la3dm_insert_pointcloud(self._h, a.ctypes.data, a.shape[0], a.strides[0], o.ctypes.data,
                                                       float(ds_resolution), float(free_res), float(max_range)))
 
+    def insert_training_data(self, xyzy):
+        """insert_training_data(xy): [n, 4] float32 host array of pre-labelled points (x y z label); BGK / GP only."""
+        a = np.ascontiguousarray(xyzy, dtype=np.float32).reshape(-1, 4)
+        self._check(self._lib.la3dm_insert_training_data(self._h, a.ctypes.data, a.shape[0], 16))
+
     def training_data(self, cloud, origin, ds_resolution, free_res=2.0, max_range=-1.0):
         """get_training_data() only: [N,7] = x0 y0 z0 x1 y1 z1 label."""
         a = np.ascontiguousarray(cloud, dtype=np.float32).reshape(-1, 3)

@@ -59,6 +59,8 @@ class RefMap:
         L.ref_max_threads.restype = C.c_int
         L.ref_insert_pointcloud.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                                             C.c_float]
+        L.ref_insert_training_data.restype = C.c_int
+        L.ref_insert_training_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.ref_num_blocks.restype = C.c_int64
         L.ref_num_blocks.argtypes = [C.c_void_p]
         L.ref_num_leaves.restype = C.c_int64
@@ -104,6 +106,13 @@ class RefMap:
         o = np.ascontiguousarray(origin, dtype=np.float32)
         self.lib.ref_insert_pointcloud(self.h, xyz.ctypes.data, xyz.shape[0], o.ctypes.data,
                                        float(ds_resolution), float(free_res), float(max_range))
+
+    def insert_training_data(self, xyzy):
+        """insert_training_data(xy), BGK / GP; every test block must already exist (upstream null dereference)."""
+        a = np.ascontiguousarray(xyzy, dtype=np.float32).reshape(-1, 4)
+        rc = self.lib.ref_insert_training_data(self.h, a.ctypes.data, a.shape[0])
+        if rc != 0:
+            raise NotImplementedError("insert_training_data: BGK / GP only")
 
     def num_blocks(self):
         return int(self.lib.ref_num_blocks(self.h))

@@ -101,6 +101,22 @@ void ref_insert_pointcloud(void *h, const float *xyz, int64_t n, const float *or
     std::cout.rdbuf(old);
 }
 
+// insert_training_data(const GPPointCloud &xy) (bgkoctomap.h:86, gpoctomap.h): BGK and GP only.  NOTE upstream
+// dereferences a null Block* for a test block that does not exist yet (bgkoctomap.cpp:155-160): callers of this
+// checker only pass points whose test blocks were created by an earlier insert_pointcloud.
+int ref_insert_training_data(void *h, const float *xyzy, int64_t n) {
+#if defined(REF_BGK) || defined(REF_GP)
+    MapT::GPPointCloud xy;
+    for (int64_t i = 0; i < n; ++i)
+        xy.emplace_back(point3f(xyzy[4 * i], xyzy[4 * i + 1], xyzy[4 * i + 2]), xyzy[4 * i + 3]);
+    static_cast<MapT *>(h)->insert_training_data(xy);
+    return 0;
+#else
+    (void) h; (void) xyzy; (void) n;
+    return -1;
+#endif
+}
+
 int64_t ref_num_blocks(void *h) { return (int64_t) static_cast<MapT *>(h)->block_arr.size(); }
 
 int64_t ref_num_leaves(void *h) {

@@ -117,3 +117,41 @@ def test_gp_error_distribution_against_compiled_reference(scans):
         # the GPU path must not be further from the reference than the restatement's own budget
         assert np.percentile(e_gpu, 99) <= max(2.0 * np.percentile(e_port, 99), 1e-4), out[-1]
     _dump("parity_gp_vs_ref.json", out)
+
+
+@needs_ref
+@pytest.mark.parametrize("method", ["bgk", "gp"])
+def test_insert_training_data_matches_compiled_reference(scans, method):
+    """insert_training_data (bgkoctomap.cpp:82-212, gpoctomap.cpp:71-203): pre-labelled points, no front-end, and for
+    BGK no `kbar > 0` guard (:179) -- every leaf of every test block becomes `classified`.  Upstream dereferences a null
+    Block* for a test block that does not exist yet (:155-160), so the blocks are created by an insert_pointcloud of
+    the same scan first; then the scan's own training set and a thinned, re-labelled copy go in as training data."""
+    import la3dm_b200
+    pts, org = scans["sim_structured"]
+    p = dict(ref.DEFAULT_PARAMS[method])
+    kw = dict(p)
+    kw["block_depth"] = int(kw["block_depth"])
+    m = la3dm_b200.maps.make_map(method, kw)
+    r = ref.RefMap(method, p, threads=1)
+    for mm in (m, r):
+        mm.insert_pointcloud(pts[0], org[0], RES, FREE_RES[method], MAX_RANGE)
+    xy = m.training_data(pts[0], org[0], RES, FREE_RES[method], MAX_RANGE)[:, [0, 1, 2, 6]]
+    thin = xy[::3].copy()
+    thin[:, 3] = np.where(np.arange(len(thin)) % 5 == 0, 1.0, thin[:, 3])      # some labels flipped to "occupied"
+    for k, td in enumerate((xy, thin)):
+        m.insert_training_data(td)
+        r.insert_training_data(td)
+        got, want = m.leaves(), oracle_leaves_as_struct(r.leaves())
+        if method == "bgk":
+            res = compare_leaves(got, want, what="bgk training data %d" % k)
+            assert res["classified_mismatch"] == 0
+            st = m.last_stats()
+            assert st["voxel_updates"] == st["voxel_visits"] > 0        # no guard: every visit is an update
+        else:
+            for f in ("block_key", "depth", "index"):
+                assert np.array_equal(got[f], want[f]), f
+            err = np.abs(got["prob"].astype(np.float64) - want["prob"])
+            assert np.percentile(err, 99) <= 2e-3 and err.max() <= 5e-2, (np.percentile(err, 99), err.max())
+    with pytest.raises(Exception):
+        la3dm_b200.BGKLOctoMap(**{k: v for k, v in ref.DEFAULT_PARAMS["bgkl"].items() if k != "block_depth"},
+                               block_depth=3).insert_training_data(xy)
