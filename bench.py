@@ -263,7 +263,7 @@ def run_ours(a):
 
     use_nccl_rows = os.environ.get("LA3DM_EXCHANGE", "peer") == "nccl"   # A/B: round 1's pack / all-gather / unpack
 
-    def new_map(params=BGK, reserve=None):
+    def new_map(params=BGK, reserve=None, deferred=False):
         m = la3dm_b200.BGKOctoMap(device=local, **params)
         if world > 1 and use_nccl_rows:
             m.set_shard(rank, world)
@@ -276,7 +276,7 @@ def run_ours(a):
                 return lst
 
             m.reserve_blocks(reserve or a.reserve_blocks)   # the pool must not move while peers are attached
-            sharding.attach_peers(m, rank, world, gather)
+            sharding.attach_peers(m, rank, world, gather, deferred=deferred)
         return m
 
     xbuf = {}
@@ -358,7 +358,9 @@ def run_ours(a):
         c_pts, c_org = make_sequence(k, 262144, 200.0, seed=5)
         d4 = [torch.from_numpy(c_pts[s]).to(dev) for s in range(k)]
         torch.cuda.synchronize()
-        m = new_map(p4, reserve=150000000)
+        # deferred peer mode: every scan rewrites most of the 3e10-byte map, so the ranks own disjoint blocks and only
+        # exchange them when the map is read (la3dm_peer_sync, timed separately below)
+        m = new_map(p4, reserve=150000000, deferred=True)
         if world == 1:
             m.reserve_blocks(150000000)       # 100 GB up front: growing a pool of this size means copying it
         ms_stream = torch.cuda.ExternalStream(m.stream(), device=dev)
@@ -375,6 +377,13 @@ def run_ours(a):
             barrier()
             ms.append(e0.elapsed_time(e1))
             st.append(m.last_stats())
+        sync_ms = None
+        if world > 1 and not use_nccl_rows:
+            barrier()
+            t0 = time.perf_counter()
+            m.peer_sync()
+            barrier()
+            sync_ms = reduce_max([1e3 * (time.perf_counter() - t0)])[0]
         m.close()
         ms = reduce_max(ms)
         upd = reduce_sum_int([x["voxel_updates"] for x in st])
@@ -386,7 +395,9 @@ def run_ours(a):
                 "first_scan_ms": ms[0], "voxel_visits_per_s": sum(vis[1:]) / T4,
                 "n_test_blocks": int(st[-1]["n_test_blocks"]), "n_train": int(st[-1]["n_train"]),
                 "predict_ms": float(np.mean(reduce_max([float(x["predict_ms"]) for x in st])[1:])),
-                "scaling": "strong", "n_gpus": world}
+                "scaling": "strong", "n_gpus": world,
+                "exchange": None if world == 1 else "deferred: owner-computes per block key, la3dm_peer_sync on read",
+                "peer_sync_ms_after_all_scans": sync_ms}
 
     timed = list(range(a.warmup, n))
     with ClockSampler(local) as clk:

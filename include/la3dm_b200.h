@@ -252,6 +252,15 @@ int la3dm_peer_ipc_open(la3dm_map *map, const void *handle_pool, const void *han
                         void **flags);
 int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bases, void *const *flags);
 int la3dm_peer_detach(la3dm_map *map);
+/* Deferred mode (set BEFORE la3dm_peer_attach): nothing crosses NVLink during a scan.  A block is owned by one rank (a
+ * fixed function of its key), only the owner updates it and marks it dirty; la3dm_peer_sync() -- collective, every
+ * rank calls it -- pushes the dirty blocks to all peers as whole records and returns when all replicas are identical
+ * again.  Between an insert and the next sync a replica holds the latest state of ITS blocks only, and the read-side
+ * calls (export, search, save, num_leaves) fail with LA3DM_ERR_INVALID.  Use it when most of the map changes every
+ * scan (BASELINE.json configs[4]: 3e10 bytes of records per scan): replicating that per scan costs more than the
+ * update itself; the default (eager) mode suits scans that touch a small part of the map. */
+int la3dm_peer_set_deferred(la3dm_map *map, int deferred);
+int la3dm_peer_sync(la3dm_map *map);
 
 /* ---- measurement helper -------------------------------------------------------------------------------------- */
 /* FP32 FMA throughput of `device` (TFLOP/s, 2 flop per FMA) from a register-resident FMA loop timed with CUDA

@@ -83,6 +83,8 @@ SYMBOLS = {
     "la3dm_peer_ipc_open": (C.c_int, [_P, _P, _P, C.POINTER(_P), C.POINTER(_P)]),
     "la3dm_peer_attach": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     "la3dm_peer_detach": (C.c_int, [_P]),
+    "la3dm_peer_set_deferred": (C.c_int, [_P, C.c_int]),
+    "la3dm_peer_sync": (C.c_int, [_P]),
     "la3dm_stream": (_P, [_P]),
     "la3dm_stream_wait": (C.c_int, [_P, _P]),
     "la3dm_bench_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),

@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(kThreads)
 k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs *__restrict__ A,
        const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
        const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask, long long *keys,
-       NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list, const unsigned int *__restrict__ tile_sums,
+       NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list, unsigned int *light_list,
+       unsigned char *dirty, const unsigned int *__restrict__ tile_sums,
        unsigned int n_tiles, int prescanned, unsigned char *pool, const DevParams *__restrict__ P, int init_records) {
     __shared__ unsigned int smem[66];
     if (c->overflow) return;
@@ -398,8 +399,9 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
         // not be overwritten by a default record that we write later; stores of one GPU to one peer arrive in order, so
         // the owner's defaults land before the owner's results.
         const PeerTable *PT = A->peers;
-        const int world = PT ? PT->world : 1, my_rank = PT ? PT->rank : 0;
-        const bool mine = (int) (t % (unsigned int) A->shard_world) == A->shard_rank || !PT;
+        const int world = (PT && !PT->deferred) ? PT->world : 1, my_rank = PT ? PT->rank : 0;
+        const bool mine = !PT || block_owner(key, t, PT->world, true) == PT->rank;
+        if (PT && PT->deferred && mine && pl.is_new) dirty[pl.slot] = 1;     // a new block reaches the peers at the next sync
         unsigned int todo = __ballot_sync(0xffffffffu, pl.is_new != 0u && mine);
         const int lane = threadIdx.x & 31;
         const int nodes = P->nodes, st_off = P->st_off, words = P->rec_bytes >> 4;
@@ -454,9 +456,11 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
         pl.count[k] = count;
         tot += count;
     }
-    // heavy blocks of this rank's shard (test block t belongs to rank t % world), predicted first
-    if (heavy_list && tot > A->heavy_tot && t % (unsigned int) A->shard_world == (unsigned int) A->shard_rank)
-        heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
+    // this rank's test blocks: the heavy ones (predicted first) and the rest
+    if (heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank) {
+        if (tot > A->heavy_tot) heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
+        else light_list[atomicAdd(&c->n_light, 1u)] = t;
+    }
     uint4 *dst = reinterpret_cast<uint4 *>(plan + t);
     const uint4 *src = reinterpret_cast<const uint4 *>(&pl);
     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
@@ -491,6 +495,11 @@ void Map::ensure_pool(size_t blocks, bool exact) {
         const size_t want = exact ? blocks : std::max((blocks > big ? blocks + blocks / 4 : 2 * blocks) + 1024, first);
         keys.grow_keep(want * sizeof(long long), stream);
         pool.grow_keep(want * (size_t) hp.rec_bytes, stream);
+        {
+            const size_t old = dirty.cap;
+            dirty.grow_keep(want, stream);
+            if (dirty.cap > old) LA3DM_CUDA(cudaMemsetAsync(dirty.as<unsigned char>() + old, 0, dirty.cap - old, stream));
+        }
         pool_cap = want;
         invalidate_graph();
     }
@@ -580,7 +589,8 @@ void Map::enqueue_binning() {
         hp.method == LA3DM_BGKL ? seg_start.as<unsigned int>() : db_start.as<unsigned int>(),
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
         hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr,
-        hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr, tile_sums, (unsigned int) p_tiles,
+        hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr, light_list.as<unsigned int>(),
+        dirty.as<unsigned char>(), tile_sums, (unsigned int) p_tiles,
         p_prescanned, pool.as<unsigned char>(), d_params, hp.method == LA3DM_BGK ? 1 : 0);
     ++launches;
     launches += 3;

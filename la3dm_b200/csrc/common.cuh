@@ -106,8 +106,20 @@ constexpr int kMaxPeers = 8;
 struct PeerTable {
     unsigned char *pool[kMaxPeers];          // pool base of every rank's replica, as mapped on THIS device ([rank]: own)
     unsigned long long *flags[kMaxPeers];    // flags[r][q], in rank r's memory: last scan that rank q has pushed completely
+                                             // ([kMaxPeers + q]: last la3dm_peer_sync rank q has pushed completely)
     int world, rank;
+    int deferred;                            // 1: no per-scan stores; the owner marks its blocks dirty, la3dm_peer_sync pushes
 };
+
+// Which replica predicts (and, with peers attached, owns) a test block.  Peers: a fixed function of the block key, so that
+// a block's state lives on one rank from scan to scan; row exchange (la3dm_shard_*): test-block index modulo world.
+__host__ __device__ inline int block_owner(long long key, unsigned int t, int world, bool by_key) {
+    if (world <= 1) return 0;
+    if (!by_key) return (int) (t % (unsigned int) world);
+    unsigned long long x = (unsigned long long) key;
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return (int) ((x >> 16) % (unsigned long long) world);
+}
 
 // Arguments of one insert_pointcloud call.  They live in device memory (copied from a pinned host mirror at the head
 // of the scan) so that every kernel of the scan has launch parameters that do not change from scan to scan -- which is
@@ -189,7 +201,7 @@ struct ScanCounters {
     unsigned int n_long_runs[2]; // voxel-grid runs handed to the long-run kernel, one CTA each
     unsigned int n_mid_runs[2];  // ... one warp each
     unsigned int grid_irregular;
-    unsigned int reserved_;      // (was: blocks after the scan -- now derived on the host from n_new_blocks)
+    unsigned int n_light;        // this rank's test blocks that are not heavy (light_list)
     unsigned int vg_cells_needed;
     unsigned int gp_n_max;       // GP: largest data block of the scan
     unsigned int lv_active;      // BGKLV: active voxels of the scan

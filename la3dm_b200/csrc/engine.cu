@@ -296,6 +296,7 @@ void Map::ensure_workspace() {
     moved |= test_id.reserve((size_t) caps.tests * 4, stream);
     moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
     moved |= heavy_list.reserve((size_t) caps.tests * 4, stream);
+    moved |= light_list.reserve((size_t) caps.tests * 4, stream);
     if (hp.method == LA3DM_BGKLV) {
         moved |= lv_range.reserve((size_t) caps.points * 8, stream);
         moved |= lv_info.reserve((size_t) caps.points * lv_ray_info_bytes(), stream);
@@ -433,7 +434,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }
 
-    if (!frontend_only) ++scan_seq;
+    if (!frontend_only) { ++scan_seq; if (peers_attached && peers_deferred) peers_unsynced = true; }
     // blocks after the scan = blocks before + blocks k_plan / k_lv_blocks created (no overflow on this path)
     n_blocks = frontend_only ? n_blocks : (long long) h_args->n_blocks + (long long) h_cnt->n_new_blocks;
     last_T = frontend_only ? 0 : h_cnt->n_test_blocks;
@@ -478,6 +479,7 @@ void Map::sorted_block_order(DevBuf &order, size_t n) {
 }
 
 void Map::export_blocks(int64_t *out_keys, la3dm_node *out_nodes, size_t cap, size_t *n_out) {
+    check_synced();
     LA3DM_CUDA(cudaSetDevice(device));
     const size_t n = (size_t) n_blocks;
     if (n_out) *n_out = n;
@@ -506,6 +508,7 @@ void Map::export_blocks(int64_t *out_keys, la3dm_node *out_nodes, size_t cap, si
 }
 
 long long Map::count_leaves() {
+    check_synced();
     LA3DM_CUDA(cudaSetDevice(device));
     const size_t n = (size_t) n_blocks;
     if (n == 0) return 0;

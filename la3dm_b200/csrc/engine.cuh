@@ -48,7 +48,7 @@ struct Map {
     DevBuf pts_sorted;              // float4 block-sorted, pre-scaled for the method's kernel
     DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
     DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
-    DevBuf test_id, plan, heavy_list;
+    DevBuf test_id, plan, heavy_list, light_list;
     DevBuf gp_sizes, gp_off, gp_store, gp_scratch, gp_mv, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
     DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists
@@ -82,7 +82,9 @@ struct Map {
     PeerTable h_peers{};
     PeerTable *d_peers = nullptr;
     DevBuf peer_flags;              // [kMaxPeers] u64, written by the peers
-    bool peers_attached = false;
+    bool peers_attached = false, peers_deferred = false, peers_unsynced = false;
+    DevBuf dirty;                   // [pool_cap] bytes: block changed since the last la3dm_peer_sync (deferred mode)
+    unsigned long long sync_seq = 0;
     unsigned long long scan_seq = 0;
 
     // ---- leaf export scratch
@@ -116,6 +118,8 @@ struct Map {
     void enqueue_gp();
     void enqueue_gp_sizes();
     void enqueue_peer_wait();
+    void peer_sync();
+    void check_synced() const;
     // export
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();

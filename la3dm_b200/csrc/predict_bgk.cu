@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(kFlatWarps * 32, LA3DM_FLAT_MIN_CTAS)
 k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
                    const long long *__restrict__ keys, unsigned char *__restrict__ pool,
                    const float3 *__restrict__ lut, const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A,
-                   ScanCounters *cnt, const unsigned int *__restrict__ heavy_list) {
+                   ScanCounters *cnt, const unsigned int *__restrict__ heavy_list,
+                   const unsigned int *__restrict__ light_list, unsigned char *__restrict__ dirty) {
     __shared__ __align__(16) FlatSmem sm[kFlatWarps];
     __shared__ DevParams Ps;
     __shared__ unsigned char *s_peer_pool[kMaxPeers];       // the other replicas' pools (multi-GPU), own rank left out
@@ -260,7 +261,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     const PeerTable *PT = A->peers;
     if (threadIdx.x == 0) {
         int n = 0;
-        if (PT)
+        if (PT && !PT->deferred)
             for (int p = 0; p < PT->world; ++p)
                 if (p != PT->rank) s_peer_pool[n++] = PT->pool[p];
         s_n_peers = n;
@@ -268,6 +269,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     __syncthreads();
     if (cnt->overflow) return;
     const int n_peers = s_n_peers;
+    const bool mark_dirty = PT && PT->deferred;
     const DevParams &P = Ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int full = 0xffffffffu, lt = (1u << lane) - 1u;
@@ -281,7 +283,6 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
     const float inv_ell = 1.0f / ell;
     const float occ_t = P.occupied_thresh, free_t = P.free_thresh, var_t = P.var_thresh;
-    const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
     // insert_training_data has no `kbar > 0` guard (bgkoctomap.cpp:179): every leaf of a test block is updated
     const bool no_guard = A->training_data != 0;
     // every leaf centre lies within (block_size - resolution) / 2 of the block centre (conservative, in units of ell)
@@ -291,14 +292,11 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     unsigned int visits = 0, updates = 0;
     unsigned long long pairs = 0;
 
-    // Work units come from one atomic counter: first the heavy blocks (more than heavy_tot neighbourhood points, listed
-    // by k_plan), one per unit, then units of kUnit consecutive test blocks of this rank (t % world == rank), the heavy
-    // ones skipped.
+    // Work units come from one atomic counter: first this rank's heavy blocks (more than heavy_tot neighbourhood
+    // points), one per unit, then units of kUnit of its other test blocks -- both listed by k_plan.
     constexpr unsigned int kUnit = 4;
-    const unsigned int heavy_tot = A->heavy_tot;
-    const unsigned int n_heavy = heavy_list ? cnt->n_heavy : 0u;
-    const unsigned int T_mine = T > shard_rank ? (T - shard_rank + shard_world - 1u) / shard_world : 0u;
-    const unsigned int units = n_heavy + (T_mine + kUnit - 1u) / kUnit;
+    const unsigned int n_heavy = cnt->n_heavy, n_light = cnt->n_light;
+    const unsigned int units = n_heavy + (n_light + kUnit - 1u) / kUnit;
     unsigned int w_next = 0;
     if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);
     for (;;) {
@@ -306,15 +304,10 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
         if (w >= units) break;
         if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);          // in flight while this unit is processed
         const bool heavy_unit = w < n_heavy;
-        const unsigned int n_in_unit = heavy_unit ? 1u : kUnit;
+        const unsigned int n_in_unit = heavy_unit ? 1u : min(kUnit, n_light - kUnit * (w - n_heavy));
 #pragma unroll 1
         for (unsigned int j = 0; j < n_in_unit; ++j) {
-            unsigned int t;
-            if (heavy_unit) t = heavy_list[w];
-            else {
-                t = (kUnit * (w - n_heavy) + j) * shard_world + shard_rank;
-                if (t >= T) break;
-            }
+            const unsigned int t = heavy_unit ? heavy_list[w] : light_list[kUnit * (w - n_heavy) + j];
             // ---- plan: lanes 0..6 hold start / count of one neighbour each
             const unsigned int plw = lane < 16 ? reinterpret_cast<const unsigned int *>(plan + t)[lane] : 0u;
             const unsigned int my_start = plw;
@@ -328,7 +321,6 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 if (lane >= o) pre += up;
             }
             const unsigned int tot = __shfl_sync(full, pre, 6);
-            if (!heavy_unit && heavy_list && tot > heavy_tot) continue;   // done in the first phase
             pre -= my_count;                                              // exclusive
             const unsigned int delta = my_start - pre;                    // point gi of neighbour k sits at gi + delta_k
             const size_t rec_off = (size_t) slot * (size_t) rec_bytes;
@@ -503,6 +495,15 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             if (lane == 0) { visits += (unsigned int) Lf; pairs += (unsigned long long) Lf * tot; }
             // ---- Occupancy::update (bgkoctree_node.cpp:31-44) for the leaves with kbar > 0 (bgkoctomap.cpp:332)
             bool changed = false, touched_any = false;
+            // Multi-GPU: a block with many updated leaves goes to the peers as ONE record (42 coalesced 16-byte stores
+            // per peer) at the end; single 8-byte stores over NVLink cost a 32-byte sector each
+            bool push_record = false;
+            if (n_peers) {
+                int nt = 0;
+                for (int lp0 = 0; lp0 < Lf; lp0 += 32)
+                    nt += __popc(__ballot_sync(full, lp0 + lane < Lf && (S.acc[lp0 + lane < Lf ? lp0 + lane : 0].y > 0.0f || no_guard)));
+                push_record = nt * 32 > rec_bytes;
+            }
 #pragma unroll 1
             for (int lp0 = 0; lp0 < Lf; lp0 += 32) {
                 const int lq = lp0 + lane;
@@ -514,8 +515,9 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                         ab.x += s.x;
                         ab.y += s.y - s.x;
                         gab[n] = ab;
-                        for (int p = 0; p < n_peers; ++p)             // the same node of the same slot in every replica
-                            reinterpret_cast<float2 *>(s_peer_pool[p] + rec_off)[n] = ab;
+                        if (!push_record)
+                            for (int p = 0; p < n_peers; ++p)         // the same node of the same slot in every replica
+                                reinterpret_cast<float2 *>(s_peer_pool[p] + rec_off)[n] = ab;
                         // get_var (bgkoctree_node.h:60) is below 1/4 for any (m_A, m_B) > 0: only evaluated if it can matter
                         unsigned int ns_ = LA3DM_UNKNOWN;
                         bool known = true;
@@ -550,8 +552,9 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                             if (same) {
                                 const float2 c0 = __ldcg(&gab[off + 8 * g]);  // parent := child 0 (classified is not copied)
                                 gab[poff + g] = c0;
-                                for (int p = 0; p < n_peers; ++p)
-                                    reinterpret_cast<float2 *>(s_peer_pool[p] + rec_off)[poff + g] = c0;
+                                if (!push_record)
+                                    for (int p = 0; p < n_peers; ++p)
+                                        reinterpret_cast<float2 *>(s_peer_pool[p] + rec_off)[poff + g] = c0;
                                 sst[poff + g] = (sst[poff + g] & 0x80) | s0;
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) sst[off + 8 * g + i] = (sst[off + 8 * g + i] & 0x80) | kStPRUNED;
@@ -566,11 +569,20 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 if (n_pruned_groups && lane == 0) sst[nodes] = (unsigned char) (Lf - 7 * n_pruned_groups);
                 __syncwarp();
             }
+            if (mark_dirty && lane == 0) dirty[slot] = 1;
             if (lane < nst_words) {
                 const unsigned int w_ = S.st[lane];
                 gst[lane] = w_;
-                for (int p = 0; p < n_peers; ++p)
-                    reinterpret_cast<unsigned int *>(s_peer_pool[p] + rec_off + st_off)[lane] = w_;
+                if (!push_record)
+                    for (int p = 0; p < n_peers; ++p)
+                        reinterpret_cast<unsigned int *>(s_peer_pool[p] + rec_off + st_off)[lane] = w_;
+            }
+            if (push_record) {
+                __syncwarp();                                        // this warp's stores to the record are visible
+                for (int w = lane; w < (rec_bytes >> 4); w += 32) {
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(rec) + w);
+                    for (int p = 0; p < n_peers; ++p) reinterpret_cast<uint4 *>(s_peer_pool[p] + rec_off)[w] = v;
+                }
             }
         }
     }
@@ -613,7 +625,8 @@ void Map::enqueue_predict() {
         if (occ < 1) occ = 1;
         kern<<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(
             plan.as<NeighbourPlan>(), pts_sorted.as<float4>(), keys.as<long long>(), pool.as<unsigned char>(), d_lut,
-            d_params, d_args, d_cnt, heavy_list.as<unsigned int>());
+            d_params, d_args, d_cnt, heavy_list.as<unsigned int>(), light_list.as<unsigned int>(),
+            dirty.as<unsigned char>());
     }
     else if (hp.depth == 4)
         k_predict_bgk_deep<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),

@@ -120,6 +120,7 @@ void Map::search(const float *xyz, size_t n, size_t stride_bytes, bool device_pt
     if (stride_bytes < 12 || stride_bytes % 4 != 0) throw StatusError{LA3DM_ERR_INVALID, "stride_bytes must be a multiple of 4, >= 12"};
     if (n > 0x7FFFFFF0ull) throw StatusError{LA3DM_ERR_INVALID, "too many query points"};
     if (n == 0) return;
+    check_synced();
     if (!xyz || !out) throw StatusError{LA3DM_ERR_INVALID, "null query / output"};
     LA3DM_CUDA(cudaSetDevice(device));
     const float *d_q = xyz;

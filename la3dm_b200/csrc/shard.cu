@@ -48,10 +48,82 @@ __global__ void k_peer_wait(const ScanArgs *__restrict__ A, ScanCounters *c, con
     __threadfence_system();
 }
 
+// Deferred mode: pushes every block this rank has changed since the last sync (only its owner ever marks a block) to all
+// peers as whole records -- a warp per 32 slots, coalesced 16-byte stores -- and clears the marks; the last CTA then
+// flags the sync as complete in every peer's memory.
+__global__ void __launch_bounds__(256)
+k_peer_sync(const PeerTable *__restrict__ PT, unsigned char *__restrict__ dirty, const unsigned char *__restrict__ pool,
+            unsigned int n_blocks, int rec_bytes, unsigned long long sync_seq, unsigned int *done_counter) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_w = (gridDim.x * blockDim.x) >> 5;
+    const int world = PT->world, rank = PT->rank, words = rec_bytes >> 4;
+    for (unsigned int base = gw * 32u; base < n_blocks; base += n_w * 32u) {
+        const unsigned int slot = base + (unsigned int) lane;
+        const bool d = slot < n_blocks && dirty[slot] != 0;
+        unsigned int todo = __ballot_sync(0xffffffffu, d);
+        if (d) dirty[slot] = 0;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const size_t off = (size_t) (base + (unsigned int) src) * (size_t) rec_bytes;
+            for (int w = lane; w < words; w += 32) {
+                const uint4 v = reinterpret_cast<const uint4 *>(pool + off)[w];
+                for (int p = 0; p < world; ++p)
+                    if (p != rank) reinterpret_cast<uint4 *>(PT->pool[p] + off)[w] = v;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+        __threadfence_system();
+        for (int p = 0; p < world; ++p)
+            if (p != rank) *reinterpret_cast<volatile unsigned long long *>(PT->flags[p] + kMaxPeers + rank) = sync_seq;
+        *done_counter = 0;
+    }
+}
+
+__global__ void k_peer_sync_wait(const PeerTable *__restrict__ PT, const unsigned long long *flags,
+                                 unsigned long long sync_seq, unsigned int *timed_out) {
+    const int p = threadIdx.x;
+    if (p >= PT->world || p == PT->rank) return;
+    const volatile unsigned long long *f = flags + kMaxPeers + p;
+    const long long t0 = clock64();
+    while (*f < sync_seq) {
+        if (clock64() - t0 > 40000000000ll) { *timed_out = 1; break; }     // ~20 s
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 }  // namespace
 
+void Map::check_synced() const {
+    if (peers_attached && peers_deferred && peers_unsynced)
+        throw StatusError{LA3DM_ERR_INVALID, "this replica holds only its own blocks' latest state: la3dm_peer_sync() "
+                                             "(on every rank) before reading the map"};
+}
+
+// collective: every rank calls it; on return all replicas are identical
+void Map::peer_sync() {
+    if (!peers_attached || !peers_deferred) return;
+    LA3DM_CUDA(cudaSetDevice(device));
+    ++sync_seq;
+    unsigned int *scratch = reinterpret_cast<unsigned int *>(peer_flags.as<unsigned long long>() + 2 * kMaxPeers);
+    LA3DM_CUDA(cudaMemsetAsync(scratch + 1, 0, 4, stream));
+    if (n_blocks > 0 || true)
+        k_peer_sync<<<num_sms * 4, 256, 0, stream>>>(d_peers, dirty.as<unsigned char>(), pool.as<unsigned char>(),
+                                                     (unsigned int) n_blocks, hp.rec_bytes, sync_seq, scratch);
+    k_peer_sync_wait<<<1, 32, 0, stream>>>(d_peers, peer_flags.as<unsigned long long>(), sync_seq, scratch + 1);
+    unsigned int timed_out = 0;
+    LA3DM_CUDA(cudaMemcpyAsync(&timed_out, scratch + 1, 4, cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    if (timed_out) throw StatusError{LA3DM_ERR_CUDA, "la3dm_peer_sync: timed out waiting for a peer"};
+    peers_unsynced = false;
+}
+
 void Map::enqueue_peer_wait() {
-    if (!peers_attached) return;
+    if (!peers_attached || peers_deferred) return;
     k_peer_wait<<<1, 32, 0, stream>>>(d_args, d_cnt, peer_flags.as<unsigned long long>());
     ++launches;
 }
@@ -99,7 +171,7 @@ static int ensure_peer_buffers(la3dm_map *map) {
     Map &m = map->m;
     if (cudaSetDevice(m.device) != cudaSuccess) return LA3DM_ERR_CUDA;
     if (!m.peer_flags.p) {
-        try { m.peer_flags.reserve(la3dm_b200::kMaxPeers * sizeof(unsigned long long), m.stream); }
+        try { m.peer_flags.reserve((2 * la3dm_b200::kMaxPeers + 1) * sizeof(unsigned long long), m.stream); }
         catch (...) { return LA3DM_ERR_NOMEM; }
         cudaMemsetAsync(m.peer_flags.p, 0, m.peer_flags.cap, m.stream);
         cudaStreamSynchronize(m.stream);
@@ -166,7 +238,7 @@ int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bas
     if (rc != LA3DM_OK) return rc;
     la3dm_b200::PeerTable &t = m.h_peers;
     memset(&t, 0, sizeof(t));
-    t.world = world; t.rank = rank;
+    t.world = world; t.rank = rank; t.deferred = m.peers_deferred ? 1 : 0;
     for (int p = 0; p < world; ++p) {
         if (p != rank && (!pool_bases[p] || !flags[p])) return LA3DM_ERR_INVALID;
         t.pool[p] = p == rank ? m.pool.as<unsigned char>() : static_cast<unsigned char *>(pool_bases[p]);
@@ -182,8 +254,24 @@ int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bas
     return LA3DM_OK;
 }
 
+int la3dm_peer_set_deferred(la3dm_map *map, int deferred) {
+    if (!map) return LA3DM_ERR_INVALID;
+    if (map->m.peers_attached) { map->m.last_error = "peer_set_deferred: call it before la3dm_peer_attach"; return LA3DM_ERR_INVALID; }
+    map->m.peers_deferred = deferred != 0;
+    return LA3DM_OK;
+}
+
+int la3dm_peer_sync(la3dm_map *map) {
+    if (!map) return LA3DM_ERR_INVALID;
+    try { map->m.peer_sync(); }
+    catch (const la3dm_b200::CudaError &e) { return peer_fail(map, "peer_sync", e.code); }
+    catch (const la3dm_b200::StatusError &e) { map->m.last_error = e.msg; return e.status; }
+    return LA3DM_OK;
+}
+
 int la3dm_peer_detach(la3dm_map *map) {
     if (!map) return LA3DM_ERR_INVALID;
+    if (map->m.peers_unsynced) { map->m.last_error = "peer_detach: la3dm_peer_sync() first"; return LA3DM_ERR_INVALID; }
     map->m.peers_attached = false;
     map->m.shard_rank = 0;
     map->m.shard_world = 1;

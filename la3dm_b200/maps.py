@@ -242,6 +242,13 @@ class _OctoMapBase:
     def peer_detach(self):
         self._check(self._lib.la3dm_peer_detach(self._h))
 
+    def peer_set_deferred(self, on=True):
+        self._check(self._lib.la3dm_peer_set_deferred(self._h, 1 if on else 0))
+
+    def peer_sync(self):
+        """Deferred mode, collective: push this rank's dirty blocks to all peers and wait for theirs."""
+        self._check(self._lib.la3dm_peer_sync(self._h))
+
 
 class BGKOctoMap(_OctoMapBase):
     METHOD = "bgk"

@@ -43,13 +43,15 @@ def exchange(map_, world, all_gather, alloc):
     return 1
 
 
-def attach_peers(map_, rank, world, all_gather_object):
+def attach_peers(map_, rank, world, all_gather_object, deferred=False):
     """BGKOctoMap, one process per GPU: exchange the CUDA IPC handles of every replica's pool / flag buffer and attach
     them, so that the predict kernel of each rank stores its results straight into all replicas (include/la3dm_b200.h,
     "multi-GPU, BGKOctoMap").  all_gather_object(obj) -> list of every rank's obj, in rank order (e.g. a closure over
     torch.distributed.all_gather_object).  Call after map_.reserve_blocks()."""
     if world == 1:
         return
+    if deferred:
+        map_.peer_set_deferred(True)
     handles = all_gather_object(map_.peer_ipc_export())
     assert len(handles) == world
     pools, flags = [0] * world, [0] * world

@@ -7,7 +7,7 @@ python - <<PY
 import json
 try:
     d = json.load(open("gpurun_out/${tag}_bench_${N}gpu.json"))
-    print("N=$N step %.4f ms" % d["ms_per_step"], "predict %.4f ms" % d["roofline"]["kernel_ms"], "e2e %.4f ms" % d["e2e"]["ms_per_step"], d.get("exchange"), d["final_leaves"])
+    print("N=$N step %.4f ms" % d["ms_per_step"], "predict %.4f ms" % d["roofline"]["kernel_ms"], "e2e %.4f ms" % d["e2e"]["ms_per_step"], d["final_leaves"], "config4:", d["config4"] if not d["config4"] or "error" in d["config4"] else (d["config4"]["ms_per_step"], d["config4"]["predict_ms"], d["config4"]["value"]))
 except Exception as e:
     print("FAILED", e)
 PY
