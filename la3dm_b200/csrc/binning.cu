@@ -370,7 +370,7 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
        const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
        const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask, long long *keys,
        NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list, unsigned int *light_list,
-       unsigned char *dirty, const unsigned int *__restrict__ tile_sums,
+       uint4 *mega_list, unsigned int *chunk_mega, unsigned char *dirty, const unsigned int *__restrict__ tile_sums,
        unsigned int n_tiles, int prescanned, unsigned char *pool, const DevParams *__restrict__ P, int init_records) {
     __shared__ unsigned int smem[66];
     if (c->overflow) return;
@@ -458,8 +458,13 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
     }
     // this rank's test blocks: the heavy ones (predicted first) and the rest
     if (heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank) {
-        if (tot > A->heavy_tot) heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
-        else light_list[atomicAdd(&c->n_light, 1u)] = t;
+        if (tot > kMegaTot) {              // cut into chunks, each predicted as a unit of its own (predict_bgk.cu)
+            const unsigned int nch = (tot + kMegaChunkPts - 1u) / kMegaChunkPts;
+            const unsigned int first = atomicAdd(&c->n_mega_chunks, nch), m = atomicAdd(&c->n_mega, 1u);
+            mega_list[m] = make_uint4(t, first, nch, 0u);
+            for (unsigned int q = 0; q < nch; ++q) chunk_mega[first + q] = m;
+        } else if (tot > A->heavy_tot) heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
+        else if (A->shard_world > 1) light_list[atomicAdd(&c->n_light, 1u)] = t;   // (one rank: walked in cell order)
     }
     uint4 *dst = reinterpret_cast<uint4 *>(plan + t);
     const uint4 *src = reinterpret_cast<const uint4 *>(&pl);
@@ -590,7 +595,7 @@ void Map::enqueue_binning() {
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
         hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr,
         hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr, light_list.as<unsigned int>(),
-        dirty.as<unsigned char>(), tile_sums, (unsigned int) p_tiles,
+        mega_list.as<uint4>(), chunk_mega.as<unsigned int>(), dirty.as<unsigned char>(), tile_sums, (unsigned int) p_tiles,
         p_prescanned, pool.as<unsigned char>(), d_params, hp.method == LA3DM_BGK ? 1 : 0);
     ++launches;
     launches += 3;

@@ -77,6 +77,8 @@ struct DevBuf {
 constexpr int kMaxDepth = 6;        // node index is unsigned short upstream (bgkoctree.cpp:9-16): fine up to depth 6
 constexpr int kMaxAxis = 8192;      // per-axis capacity of the float-stepped block grid (blocks per axis per scan)
 constexpr unsigned int kHeavyTot = 64;   // test blocks above this many neighbourhood points are predicted first
+constexpr unsigned int kMegaTot = 2048;  // ... above this many they are cut into chunks predicted by several warps
+constexpr unsigned int kMegaChunkPts = 256;
 constexpr int kStPRUNED = 3;        // BGK/BGKL/GP numbering; BGKLV uses 4 (see include/la3dm_b200.h)
 
 struct DevParams {
@@ -143,6 +145,7 @@ struct ScanArgs {
     unsigned int heavy_tot; // test blocks with more neighbourhood points than this are predicted first (kHeavyTot)
     const PeerTable *peers; // attached replicas (nullptr: none)
     unsigned long long scan_seq;   // sequence number of this scan (peer completion flags)
+    int ab_flags;           // A/B switches for profiling (LA3DM_AB), 0 in production
 };
 
 // per-scan block grid: restates get_blocks_in_bbox (src/bgkoctomap/bgkoctomap.cpp:486-495) as a Cartesian product of
@@ -202,6 +205,7 @@ struct ScanCounters {
     unsigned int n_mid_runs[2];  // ... one warp each
     unsigned int grid_irregular;
     unsigned int n_light;        // this rank's test blocks that are not heavy (light_list)
+    unsigned int n_mega, n_mega_chunks, work_next2, work_next3;   // mega blocks (kMegaTot) and their chunks
     unsigned int vg_cells_needed;
     unsigned int gp_n_max;       // GP: largest data block of the scan
     unsigned int lv_active;      // BGKLV: active voxels of the scan

@@ -297,6 +297,14 @@ void Map::ensure_workspace() {
     moved |= plan.reserve((size_t) caps.tests * sizeof(NeighbourPlan), stream);
     moved |= heavy_list.reserve((size_t) caps.tests * 4, stream);
     moved |= light_list.reserve((size_t) caps.tests * 4, stream);
+    if (hp.method == LA3DM_BGK) {
+        // mega blocks (> kMegaTot neighbourhood points) and their chunks: sum of tot over all test blocks = 7 * members
+        const size_t n_mega_cap = (size_t) 7 * caps.members / kMegaTot + 8;
+        const size_t n_chunk_cap = (size_t) 7 * caps.members / kMegaChunkPts + n_mega_cap;
+        moved |= mega_list.reserve(n_mega_cap * sizeof(uint4), stream);
+        moved |= chunk_mega.reserve(n_chunk_cap * 4, stream);
+        moved |= mega_acc.reserve(n_chunk_cap * 64 * sizeof(float2), stream);
+    }
     if (hp.method == LA3DM_BGKLV) {
         moved |= lv_range.reserve((size_t) caps.points * 8, stream);
         moved |= lv_info.reserve((size_t) caps.points * lv_ray_info_bytes(), stream);
@@ -376,6 +384,8 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.heavy_tot = heavy_tot;
         a.peers = (peers_attached && !frontend_only) ? d_peers : nullptr;
         a.scan_seq = scan_seq + 1;
+        static const int ab = getenv("LA3DM_AB") ? atoi(getenv("LA3DM_AB")) : 0;
+        a.ab_flags = ab;
 
         LA3DM_CUDA(cudaEventRecord(ev0, stream));
         LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));

@@ -48,7 +48,7 @@ struct Map {
     DevBuf pts_sorted;              // float4 block-sorted, pre-scaled for the method's kernel
     DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
     DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
-    DevBuf test_id, plan, heavy_list, light_list;
+    DevBuf test_id, plan, heavy_list, light_list, mega_list, chunk_mega, mega_acc;
     DevBuf gp_sizes, gp_off, gp_store, gp_scratch, gp_mv, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
     DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists

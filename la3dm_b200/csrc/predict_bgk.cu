@@ -245,19 +245,22 @@ __device__ __forceinline__ float sparse_kernel_d2(float d2, float sf2) {
     return k < 0.0f ? 0.0f : k;      // bgkinference.h:120-125
 }
 
-template <bool kD3>
+// kMode 0: whole blocks (heavy list, then light list); 1: the chunks of the mega blocks -> partial sums; 2: the mega
+// blocks are finished from their partial sums (also signals the peers: it is the last launch of the scan).
+template <bool kD3, int kMode>
 __global__ void __launch_bounds__(kFlatWarps * 32, LA3DM_FLAT_MIN_CTAS)
 k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
                    const long long *__restrict__ keys, unsigned char *__restrict__ pool,
                    const float3 *__restrict__ lut, const DevParams *__restrict__ Pg, const ScanArgs *__restrict__ A,
                    ScanCounters *cnt, const unsigned int *__restrict__ heavy_list,
-                   const unsigned int *__restrict__ light_list, unsigned char *__restrict__ dirty) {
+                   const unsigned int *__restrict__ light_list, unsigned char *__restrict__ dirty,
+                   const uint4 *__restrict__ mega_list, const unsigned int *__restrict__ chunk_mega, float2 *mega_acc) {
     __shared__ __align__(16) FlatSmem sm[kFlatWarps];
     __shared__ DevParams Ps;
     __shared__ unsigned char *s_peer_pool[kMaxPeers];       // the other replicas' pools (multi-GPU), own rank left out
     __shared__ int s_n_peers;
-    if (threadIdx.x < sizeof(DevParams) / 4)
-        reinterpret_cast<int *>(&Ps)[threadIdx.x] = reinterpret_cast<const int *>(Pg)[threadIdx.x];
+    for (unsigned int i = threadIdx.x; i < sizeof(DevParams) / 4; i += blockDim.x)
+        reinterpret_cast<int *>(&Ps)[i] = reinterpret_cast<const int *>(Pg)[i];
     const PeerTable *PT = A->peers;
     if (threadIdx.x == 0) {
         int n = 0;
@@ -268,7 +271,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     }
     __syncthreads();
     if (cnt->overflow) return;
-    const int n_peers = s_n_peers;
+    const int n_peers = kMode == 1 ? 0 : s_n_peers;
     const bool mark_dirty = PT && PT->deferred;
     const DevParams &P = Ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -295,19 +298,37 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     // Work units come from one atomic counter: first this rank's heavy blocks (more than heavy_tot neighbourhood
     // points), one per unit, then units of kUnit of its other test blocks -- both listed by k_plan.
     constexpr unsigned int kUnit = 4;
-    const unsigned int n_heavy = cnt->n_heavy, n_light = cnt->n_light;
-    const unsigned int units = n_heavy + (n_light + kUnit - 1u) / kUnit;
+    // A MEGA block (more than kMegaTot neighbourhood points: the sensor's own block holds one copy of the origin per
+    // hit when the voxel grid passes its input through) is cut into chunks of kMegaChunkPts points, each a unit of its own
+    // that leaves per-leaf partial sums in mega_acc; a second launch (phase 1) adds the partial sums of a block in chunk
+    // order and finishes it.  Left to one warp such a block outlasts the rest of the scan.
+    constexpr int mode = kMode;
+    const unsigned int n_mc = kMode == 1 ? cnt->n_mega_chunks : 0u, n_mega = kMode == 2 ? cnt->n_mega : 0u;
+    // one rank owns every block: the test blocks are walked in cell order (neighbours in space are neighbours in time: their
+    // shared training points are still in L2), the heavy / mega ones skipped; several ranks: this rank's list from k_plan
+    const bool ab_order = kMode == 0 && A->shard_world == 1;
+    const unsigned int n_heavy = kMode == 0 ? cnt->n_heavy : 0u, n_light = kMode == 0 ? (ab_order ? T : cnt->n_light) : 0u;
+    const unsigned int units = kMode == 0 ? n_heavy + (n_light + kUnit - 1u) / kUnit : (kMode == 1 ? n_mc : n_mega);
+    unsigned int *work_ctr = kMode == 0 ? &cnt->work_next : (kMode == 1 ? &cnt->work_next2 : &cnt->work_next3);
     unsigned int w_next = 0;
-    if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);
+    if (lane == 0) w_next = atomicAdd(work_ctr, 1u);
     for (;;) {
         const unsigned int w = __shfl_sync(full, w_next, 0);
         if (w >= units) break;
-        if (lane == 0) w_next = atomicAdd(&cnt->work_next, 1u);          // in flight while this unit is processed
-        const bool heavy_unit = w < n_heavy;
-        const unsigned int n_in_unit = heavy_unit ? 1u : min(kUnit, n_light - kUnit * (w - n_heavy));
+        if (lane == 0) w_next = atomicAdd(work_ctr, 1u);                 // in flight while this unit is processed
+        const bool heavy_unit = kMode == 0 && w < n_heavy;
+        const unsigned int lw = w - n_heavy;                             // light unit index (mode 0, not heavy)
+        const unsigned int n_in_unit = (kMode != 0 || heavy_unit) ? 1u : min(kUnit, n_light - kUnit * lw);
 #pragma unroll 1
         for (unsigned int j = 0; j < n_in_unit; ++j) {
-            const unsigned int t = heavy_unit ? heavy_list[w] : light_list[kUnit * (w - n_heavy) + j];
+            unsigned int t, c_lo = 0u, c_hi = 0xFFFFFFFFu, mega_first = 0u, mega_chunks = 0u;
+            if (kMode == 0) t = heavy_unit ? heavy_list[w] : (ab_order ? kUnit * lw + j : light_list[kUnit * lw + j]);
+            else {
+                const uint4 mg = mega_list[kMode == 1 ? chunk_mega[w] : w];  // (t, first chunk, chunks, -)
+                t = mg.x; mega_first = mg.y; mega_chunks = mg.z;
+                if (kMode == 1) { c_lo = (w - mg.y) * kMegaChunkPts; c_hi = c_lo + kMegaChunkPts; }
+                else c_hi = 0u;                                          // finish: no points to walk
+            }
             // ---- plan: lanes 0..6 hold start / count of one neighbour each
             const unsigned int plw = lane < 16 ? reinterpret_cast<const unsigned int *>(plan + t)[lane] : 0u;
             const unsigned int my_start = plw;
@@ -321,6 +342,8 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 if (lane >= o) pre += up;
             }
             const unsigned int tot = __shfl_sync(full, pre, 6);
+            if (kMode == 0 && ab_order && !heavy_unit && tot > A->heavy_tot) continue;   // in the heavy / mega list
+            const unsigned int p_end = min(tot, c_hi);                    // this unit walks points [c_lo, p_end)
             pre -= my_count;                                              // exclusive
             const unsigned int delta = my_start - pre;                    // point gi of neighbour k sits at gi + delta_k
             const size_t rec_off = (size_t) slot * (size_t) rec_bytes;
@@ -337,11 +360,11 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
 #pragma unroll
                 for (int k = 1; k < 7; ++k) nbi += (gi >= __shfl_sync(full, pre, k)) ? 1u : 0u;
                 const unsigned int d = __shfl_sync(full, delta, (int) nbi);
-                if (gi < tot) { z = pts[gi + d]; return true; }
+                if (gi < p_end) { z = pts[gi + d]; return true; }
                 return false;
             };
             float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool valid = fetch(0, z);
+            bool valid = fetch(c_lo, z);
             // block centre from its key (hash_key_to_block, bgkblock.cpp:79-83); the hull test may round differently
             const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
                         cz = axis_center(key & 0xFFFFF, bs);
@@ -381,9 +404,11 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             };
 
             unsigned int ns = 0;                                          // survivors staged in S.pt
+            // (mode 1 and 2 list the leaves even without a survivor: their sums are written / read per leaf position)
+            const bool force_leaves = no_guard || mode != 0;
 #pragma unroll 1
-            for (unsigned int base = 0; base < tot; base += 32) {
-                if (base) valid = fetch(base, z);
+            for (unsigned int base = c_lo; base < p_end || (force_leaves && Lf < 0); base += 32) {
+                if (base != c_lo) valid = fetch(base, z);
                 bool keep = false;
                 if (valid) {
                     const float rx = fmaxf(fabsf(z.x - ccx) - reach, 0.f), ry = fmaxf(fabsf(z.y - ccy) - reach, 0.f),
@@ -393,8 +418,8 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 const unsigned int kept = __ballot_sync(full, keep);
                 if (keep) S.pt[ns + __popc(kept & lt)] = z;
                 ns += __popc(kept);
-                const bool last = base + 32 >= tot;
-                if ((ns == 0 && !(no_guard && last && Lf < 0)) || (!last && ns <= (unsigned int) (kFlatPts - 32))) continue;
+                const bool last = base + 32 >= p_end;
+                if ((ns == 0 && !(force_leaves && last && Lf < 0)) || (!last && ns <= (unsigned int) (kFlatPts - 32))) continue;
                 // ---- list the block's leaves once: centre / ell and node index; zero their accumulators
                 if (Lf < 0) {
                     if (kD3) {
@@ -483,6 +508,22 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 }
                 if (qt != qh) drain(qt - qh);
                 ns = 0;
+                __syncwarp();
+            }
+            if (mode == 1) {        // partial sums of this chunk, per leaf position
+                float2 *dst = mega_acc + (size_t) w * 64;
+                for (int lq = lane; lq < Lf; lq += 32) dst[lq] = S.acc[lq];
+                continue;
+            }
+            if (mode == 2) {        // the block's sums = its chunks' partial sums added in chunk order
+                for (int lq = lane; lq < Lf; lq += 32) {
+                    float2 a = make_float2(0.f, 0.f);
+                    for (unsigned int c = 0; c < mega_chunks; ++c) {
+                        const float2 v = mega_acc[(size_t) (mega_first + c) * 64 + lq];
+                        a.x += v.x; a.y += v.y;
+                    }
+                    S.acc[lq] = a;
+                }
                 __syncwarp();
             }
             // ---- statistics; a block no training point can reach is done (its leaf count sits behind the states)
@@ -599,8 +640,9 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
         atomicAdd(&cnt->updates, u64);
         atomicAdd(&cnt->pairs, pairs);
     }
-    // ---- multi-GPU: when the last CTA has pushed its results, tell every peer that this rank is done with the scan
-    if (n_peers) {
+    // ---- multi-GPU: when the last CTA (of the second pass) has pushed its results, tell every peer that this rank is
+    // done with the scan
+    if (n_peers && kMode == 2) {
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0 && atomicAdd(&cnt->ctas_done, 1u) == gridDim.x - 1) {
@@ -619,14 +661,26 @@ void Map::enqueue_predict() {
     const int ctas = num_sms * 4;
     record_event(ev_p0);
     if (hp.depth <= 3) {
-        auto kern = hp.depth == 3 ? k_predict_bgk_flat<true> : k_predict_bgk_flat<false>;
+        // three launches: whole blocks; then (usually empty) the chunks of the mega blocks and their completion
+#define LA3DM_FLAT_ARGS plan.as<NeighbourPlan>(), pts_sorted.as<float4>(), keys.as<long long>(), pool.as<unsigned char>(), d_lut, \
+            d_params, d_args, d_cnt, heavy_list.as<unsigned int>(), light_list.as<unsigned int>(), \
+            dirty.as<unsigned char>(), mega_list.as<uint4>(), chunk_mega.as<unsigned int>(), mega_acc.as<float2>()
         int occ = 0;
-        LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFlatWarps * 32, 0));
-        if (occ < 1) occ = 1;
-        kern<<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(
-            plan.as<NeighbourPlan>(), pts_sorted.as<float4>(), keys.as<long long>(), pool.as<unsigned char>(), d_lut,
-            d_params, d_args, d_cnt, heavy_list.as<unsigned int>(), light_list.as<unsigned int>(),
-            dirty.as<unsigned char>());
+        if (hp.depth == 3) {
+            LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_predict_bgk_flat<true, 0>, kFlatWarps * 32, 0));
+            if (occ < 1) occ = 1;
+            k_predict_bgk_flat<true, 0><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+            k_predict_bgk_flat<true, 1><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+            k_predict_bgk_flat<true, 2><<<num_sms, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+        } else {
+            LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_predict_bgk_flat<false, 0>, kFlatWarps * 32, 0));
+            if (occ < 1) occ = 1;
+            k_predict_bgk_flat<false, 0><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+            k_predict_bgk_flat<false, 1><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+            k_predict_bgk_flat<false, 2><<<num_sms, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+        }
+#undef LA3DM_FLAT_ARGS
+        launches += 2;
     }
     else if (hp.depth == 4)
         k_predict_bgk_deep<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
