@@ -144,6 +144,18 @@ int la3dm_insert_pointcloud(la3dm_map *map, const float *xyz, size_t n, size_t s
 int la3dm_insert_pointcloud_device(la3dm_map *map, const float *d_xyz, size_t n, size_t stride_bytes,
                                    const float origin[3], float ds_resolution, float free_res, float max_range);
 
+/* The live node's steps in front of insert_pointcloud, fused into the GPU front-end (cloudHandler,
+ * src/bgkoctomap/bgkoctomap_server.cpp:70-86 and the -L/GP copies; the -LV server skips the prefilter,
+ * bgklvoctomap_server.cpp:76-77): the sensor-frame cloud is moved into the map frame by tf (pcl_ros::
+ * transformPointCloud; 3 x 4 row-major, fp32, evaluated like pcl::transformPointCloud), downsampled by a
+ * pcl::VoxelGrid of leaf prefilter_ds (<= 0: no prefilter), and inserted only if more than min_points points are left
+ * (upstream: 5) -- otherwise the call is a no-op, like upstream's `if (filtered_cloud.size() > 5)`.  origin is the
+ * translation of the transform, as upstream passes it; ds_resolution / free_res / max_range are insert_pointcloud's.
+ * The TF lookup and the motion gate (:46-60) stay with the caller: they are ROS calls, not arithmetic on the cloud. */
+int la3dm_insert_pointcloud_ingest(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, const float tf[12],
+                                   float prefilter_ds, int min_points, const float origin[3], float ds_resolution,
+                                   float free_res, float max_range);
+
 /* Replaces  void insert_training_data(const GPPointCloud &xy)  (include/bgkoctomap/bgkoctomap.h:86,
  * src/bgkoctomap/bgkoctomap.cpp:82-212; include/gpoctomap/gpoctomap.h, src/gpoctomap/gpoctomap.cpp:71-203): the same
  * update WITHOUT the front-end -- the caller's pre-labelled points are the training set.  xyzy: n records of
@@ -194,6 +206,18 @@ int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t
  * LEAF containing the point.  The cell index uses cell_num = 2^(block_depth-1): upstream freezes Block::cell_num at 8
  * during static initialisation (bgkblock.cpp:105), which is only right for block_depth 4. */
 int la3dm_search(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, int finest_only, la3dm_leaf *out);
+
+/* Ray casting, batched: replaces  class RayCaster { RayCaster(map, start, end); bool end(); bool next(p, node, block_key,
+ * node_key); }  (include/bgkoctomap/bgkoctomap.h:91-214 and the -L/-LV/GP copies) -- the integer walk over the finest
+ * cells from start to end, crossing blocks.  start_end: n_rays HOST records of 6 floats (start xyz, end xyz).  Step i of
+ * ray r lands in out[r * max_steps + i] (HOST), n_steps[r] of them (the walk is cut at max_steps): what next() hands back
+ * -- block_key, the finest node of the cell (depth = block_depth - 1, index; PRUNED or not, like operator[]), x y z =
+ * Block::get_point, the node's floats / state / probability; where the block does not exist next() returns false: depth
+ * = -1 and x y z = the position tracked so far.  A ray whose start block does not exist has no steps (upstream: n = 0).
+ * Upstream's step accounting is kept as written (an xy tie consumes three counts, a step may not move).  Cell indices
+ * use 2^(block_depth-1) cells per axis (see la3dm_search about Block::cell_num). */
+int la3dm_raycast(la3dm_map *map, const float *start_end, size_t n_rays, size_t max_steps, la3dm_leaf *out,
+                  int32_t *n_steps);
 
 /* Inverse of la3dm_export_blocks: fills an EMPTY map from HOST arrays in the reference's Block/OcTree layout
  * (keys[i], nodes[i * nodes_per_block + ...]); afterwards scans can be inserted as if the map had been built here. */

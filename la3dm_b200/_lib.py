@@ -53,6 +53,8 @@ SYMBOLS = {
     "la3dm_insert_pointcloud": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float, C.c_float]),
     "la3dm_insert_pointcloud_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float,
                                                  C.c_float]),
+    "la3dm_insert_pointcloud_ingest": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_int, _P, C.c_float,
+                                                C.c_float, C.c_float]),
     "la3dm_insert_training_data": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
     "la3dm_insert_training_data_device": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
     "la3dm_training_data": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, C.c_float, C.c_float, C.c_float, _P,
@@ -65,6 +67,7 @@ SYMBOLS = {
     "la3dm_num_leaves": (C.c_int64, [_P]),
     "la3dm_export_leaves": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "la3dm_search": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, _P]),
+    "la3dm_raycast": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
     "la3dm_import_blocks": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "la3dm_save": (C.c_int, [_P, C.c_char_p]),
     "la3dm_load": (C.c_int, [_P, C.c_char_p]),

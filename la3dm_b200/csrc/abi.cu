@@ -104,6 +104,25 @@ int la3dm_insert_pointcloud(la3dm_map *map, const float *xyz, size_t n, size_t s
     });
 }
 
+int la3dm_insert_pointcloud_ingest(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, const float tf[12],
+                                   float prefilter_ds, int min_points, const float origin[3], float ds_resolution,
+                                   float free_res, float max_range) {
+    if (!map || !origin || !tf || (n && !xyz)) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] {
+        Map &m = map->m;
+        LA3DM_CUDA(cudaSetDevice(m.device));
+        if (stride_bytes < 12 || stride_bytes % 4) throw la3dm_b200::StatusError{LA3DM_ERR_INVALID, "bad stride_bytes"};
+        m.cloud.reserve(n * stride_bytes + 16, m.stream);
+        if (n) LA3DM_CUDA(cudaMemcpyAsync(m.cloud.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, m.stream));
+        m.h2d_bytes = (long long) (n * stride_bytes);
+        if (m.ingest_pre_ds != prefilter_ds) m.invalidate_graph();      // with / without the prefilter: other kernels
+        memcpy(m.ingest_tf, tf, sizeof(m.ingest_tf));
+        m.ingest_pre_ds = prefilter_ds;
+        m.ingest_min_points = min_points;
+        m.insert_device(m.cloud.as<float>(), n, stride_bytes, origin, ds_resolution, free_res, max_range, 3);
+    });
+}
+
 int la3dm_insert_training_data(la3dm_map *map, const float *xyzy, size_t n, size_t stride_bytes) {
     if (!map || (n && !xyzy)) return LA3DM_ERR_INVALID;
     return guarded(map, [&] {
@@ -208,6 +227,12 @@ int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t
 int la3dm_search(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, int finest_only, la3dm_leaf *out) {
     if (!map) return LA3DM_ERR_INVALID;
     return guarded(map, [&] { map->m.search(xyz, n, stride_bytes, false, finest_only, out); });
+}
+
+int la3dm_raycast(la3dm_map *map, const float *start_end, size_t n_rays, size_t max_steps, la3dm_leaf *out,
+                  int32_t *n_steps) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] { map->m.raycast(start_end, n_rays, max_steps, out, n_steps); });
 }
 
 int la3dm_import_blocks(la3dm_map *map, const int64_t *keys, const la3dm_node *nodes, size_t n_blocks) {

@@ -146,6 +146,14 @@ struct ScanArgs {
     const PeerTable *peers; // attached replicas (nullptr: none)
     unsigned long long scan_seq;   // sequence number of this scan (peer completion flags)
     int ab_flags;           // A/B switches for profiling (LA3DM_AB), 0 in production
+    // ingest (server-side steps before insert_pointcloud, bgkoctomap_server.cpp:70-86): sensor-frame cloud -> map frame
+    // by tf (3 x 4 row-major), VoxelGrid prefilter at pre_ds, scan skipped unless more than min_points survive
+    const float *raw_xyz;   // the caller's cloud (sensor frame)
+    int raw_stride_f;
+    float tf[12];
+    float scan_ds, scan_inv_ds;   // ds_resolution of the insert_pointcloud that follows the prefilter
+    int min_points;
+    float4 *stage_cloud;    // transformed cloud, then the prefiltered one
 };
 
 // per-scan block grid: restates get_blocks_in_bbox (src/bgkoctomap/bgkoctomap.cpp:486-495) as a Cartesian product of

@@ -375,6 +375,17 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
         a.ds = ds; a.inv_ds = 1.0f / ds; a.fr = fr; a.max_range = max_range;
         a.free_label = hp.method == LA3DM_GP ? -1.0f : 0.0f;   // src/gpoctomap/gpoctomap.cpp:399
+        if (mode == 3) {
+            // stage 1 of the ingest reads the transformed cloud with the prefilter's leaf size; k_ingest_commit then
+            // switches the arguments to the prefiltered cloud and the scan's own ds_resolution
+            if (stage_cloud.reserve((size_t) caps.points * sizeof(float4), stream)) invalidate_graph();
+            a.raw_xyz = d_xyz; a.raw_stride_f = (int) (stride_bytes / 4);
+            for (int q = 0; q < 12; ++q) a.tf[q] = ingest_tf[q];
+            a.scan_ds = ds; a.scan_inv_ds = 1.0f / ds; a.min_points = ingest_min_points;
+            a.stage_cloud = stage_cloud.as<float4>();
+            a.xyz = stage_cloud.as<float>(); a.stride_f = 4;
+            if (ingest_pre_ds > 0) { a.ds = ingest_pre_ds; a.inv_ds = 1.0f / ingest_pre_ds; }
+        }
         a.frontend_only = frontend_only ? 1 : 0;
         a.training_data = training ? 1 : 0;
         a.shard_rank = shard_rank; a.shard_world = shard_world;

@@ -41,6 +41,7 @@ struct Map {
     // ---- per-scan workspace, sized by `caps`
     Caps caps{};                    // logical capacities the scan kernels check against
     DevBuf cloud;                   // uploaded scan (host entry point)
+    DevBuf stage_cloud;             // ingest: transformed / prefiltered cloud (float4)
     DevBuf sort_keys[2], sort_vals[2], run_start, cub_tmp, tiles, long_list, long_flags, hit_cnt;
     DevBuf hits_ds;                 // float4 voxel-grid output of the cloud
     DevBuf frees_raw;               // float4 beam samples
@@ -99,12 +100,17 @@ struct Map {
     void ensure_beam_table(float fr);
     void invalidate_graph();
     void record_event(cudaEvent_t ev);   // inside or outside of a stream capture
-    // mode: 0 insert_pointcloud, 1 front-end only (get_training_data), 2 insert_training_data (d_xyz = x y z label)
+    // mode: 0 insert_pointcloud, 1 front-end only (get_training_data), 2 insert_training_data (d_xyz = x y z label),
+    //       3 ingest (tf transform + prefilter from ingest_*) then insert_pointcloud
     void insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const float origin[3], float ds, float fr,
                        float max_range, int mode);
     // the scan, enqueued on `stream` without host synchronisation (graph-capturable)
     void enqueue_scan(int mode);
     void enqueue_training_data();
+    void enqueue_ingest();
+    float ingest_tf[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    float ingest_pre_ds = -1.f;
+    int ingest_min_points = 0;
     void enqueue_frontend_bgk();
     void enqueue_frontend_bgkl();
     void enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int *sorted_vals);
@@ -127,6 +133,7 @@ struct Map {
     void sorted_block_order(DevBuf &order, size_t n);
     // query / import / serialisation (query.cu)
     void search(const float *xyz, size_t n, size_t stride_bytes, bool device_ptr, int finest_only, la3dm_leaf *out);
+    void raycast(const float *start_end, size_t n_rays, size_t max_steps, la3dm_leaf *out, int32_t *n_steps);
     void import_blocks(const int64_t *keys, const la3dm_node *nodes, size_t n);
     void rebuild_hash();
     void save(const char *path);

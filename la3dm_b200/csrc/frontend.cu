@@ -629,6 +629,43 @@ __global__ void k_td_load(const ScanArgs *__restrict__ A, ScanCounters *c, float
     block_minmax_box(any, mn, mx, mm_xy, s_mm);
 }
 
+// ---- ingest: the server-side steps in front of insert_pointcloud (src/bgkoctomap/bgkoctomap_server.cpp:70-86) --------
+// pcl_ros::transformPointCloud -> pcl::transformPointCloud(cloud, Eigen::Matrix4f): p' = T p in fp32, evaluated like
+// pcl::detail::Transformer (PCL >= 1.10): (m0 x + m1 y) + (m2 z + m3) per row, products and sums rounded separately.
+// (PCL is a third-party dependency absent from /root/reference: this seam is "parity unpinned", see DESIGN.md.)
+__global__ void k_tf_points(const ScanArgs *__restrict__ A, float4 *out) {
+    const unsigned int n = A->n;
+    const float *m = A->tf;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *p = A->raw_xyz + (size_t) i * A->raw_stride_f;
+        const float x = p[0], y = p[1], z = p[2];
+        out[i] = make_float4((m[0] * x + m[1] * y) + (m[2] * z + m[3]), (m[4] * x + m[5] * y) + (m[6] * z + m[7]),
+                             (m[8] * x + m[9] * y) + (m[10] * z + m[11]), 0.f);
+    }
+}
+
+// after the prefilter's voxel grid: the filtered cloud (hits_ds) becomes the scan's cloud if more than min_points
+// points are left (bgkoctomap_server.cpp:84: `if (filtered_cloud.size() > 5)`), else the scan is empty; the counters the
+// prefilter used are reset for the scan proper (overflow bits are kept)
+__global__ void k_ingest_commit(ScanArgs *A, ScanCounters *c, unsigned int *mm, const float4 *__restrict__ filtered,
+                                int prefiltered) {
+    __shared__ unsigned int s_n;
+    if (threadIdx.x == 0) s_n = prefiltered ? c->n_ds_hits : A->n;
+    __syncthreads();
+    const unsigned int n = s_n;
+    if (prefiltered)
+        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            A->stage_cloud[i] = filtered[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned int ovf = c->overflow;
+        *c = ScanCounters();
+        c->overflow = ovf;
+        A->n = n > (unsigned int) max(A->min_points, 0) ? n : 0u;
+        A->ds = A->scan_ds; A->inv_ds = A->scan_inv_ds;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 18) mm[threadIdx.x] = (threadIdx.x % 6) < 3 ? 0xFFFFFFFFu : 0u;
+}
+
 inline int bits_for(unsigned int n) {   // radix-sort end bit for keys < n
     int b = 1;
     while (b < 32 && (1ull << b) < (unsigned long long) n) ++b;
@@ -713,11 +750,24 @@ void Map::enqueue_training_data() {
     ++launches;
 }
 
+// transform + prefilter; leaves d_args describing the cloud insert_pointcloud proper starts from
+void Map::enqueue_ingest() {
+    const int grid = std::max(1, std::min(ceil_div(caps.points, kThreads), num_sms * 8));
+    k_tf_points<<<grid, kThreads, 0, stream>>>(d_args, stage_cloud.as<float4>());
+    ++launches;
+    const int pre = ingest_pre_ds > 0 ? 1 : 0;
+    if (pre) enqueue_voxel_grid(0);               // stage_cloud --(leaf = pre_ds)--> hits_ds, count in n_ds_hits
+    // (single CTA: the copy must not race with the counter reset, and a prefiltered cloud is small)
+    k_ingest_commit<<<1, 1024, 0, stream>>>(d_args, d_cnt, d_mm, hits_ds.as<float4>(), pre);
+    ++launches;
+}
+
 void Map::enqueue_scan(int mode) {
     const bool frontend_only = mode == 1;
     launches = 0;
     k_scan_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm);
     ++launches;
+    if (mode == 3) enqueue_ingest();
     if (mode == 2) enqueue_training_data();
     else if (hp.method == LA3DM_BGKL) enqueue_frontend_bgkl();
     else if (hp.method == LA3DM_BGKLV) enqueue_frontend_lv();

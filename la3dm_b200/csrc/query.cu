@@ -71,6 +71,93 @@ __global__ void k_search(const float *__restrict__ q, unsigned int n, int stride
     out[i] = make_leaf(P, key, d, idx, bab[node], bst[node], lut[node], cx, cy, cz);
 }
 
+// BGKOctoMap::RayCaster (include/bgkoctomap/bgkoctomap.h:91-214 and the -L/-LV/GP copies): the integer walk over the
+// finest cells between two points, crossing blocks, one thread per ray.  Everything -- including the step accounting
+// (`n -= 2` plus `n--` on an xy tie, a step without a move when no branch matches) and the unsigned-short wrap of a
+// cell index stepping below 0 -- follows upstream statement by statement; cell indices use cell_num = 2^(depth-1) like
+// la3dm_search (upstream mixes `lim` with the frozen Block::cell_num, identical at block_depth 4).
+// Step i of ray r -> out[r * max_steps + i]: the finest node of the cell (what operator[] returns, PRUNED or not) as a
+// leaf record with x y z = Block::get_point; where the block does not exist: depth = -1, x y z = the tracked position.
+__global__ void k_raycast(const float *__restrict__ se, unsigned int n_rays, unsigned int max_steps,
+                          const long long *__restrict__ hkeys, const int *__restrict__ hvals, size_t mask,
+                          const unsigned char *__restrict__ pool, const float3 *__restrict__ lut,
+                          const DevParams *__restrict__ Pg, la3dm_leaf *out, int *n_steps) {
+    const unsigned int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const DevParams &P = *Pg;
+    const float sx = se[6 * r], sy = se[6 * r + 1], sz = se[6 * r + 2];
+    const float ex = se[6 * r + 3], ey = se[6 * r + 4], ez = se[6 * r + 5];
+    const float bs = P.block_size, res = P.resolution;
+    const int lim = 1 << (P.depth - 1), half = lim / 2;
+    long long key = make_key(axis_index(sx, bs), axis_index(sy, bs), axis_index(sz, bs));
+    int slot = hash_find(hkeys, hvals, mask, key);
+    la3dm_leaf *o = out + (size_t) r * max_steps;
+    int steps = 0;
+    if (slot < 0) { n_steps[r] = 0; return; }                    // upstream: n = 0 when the start block does not exist
+    // hash_key_to_block of the start block = block->get_center()
+    float blx = axis_center(key >> 40, bs), bly = axis_center((key >> 20) & 0xFFFFF, bs), blz = axis_center(key & 0xFFFFF, bs);
+    float bcx = blx, bcy = bly, bcz = blz;                       // centre of the CURRENT block (get_point)
+    // Block::get_index (bgkblock.cpp:139-147)
+    auto clip = [&](int a) { return max(0, min(a, lim - 1)); };
+    unsigned short x = (unsigned short) clip((int) ((sx - blx) / res + (float) half));
+    unsigned short y = (unsigned short) clip((int) ((sy - bly) / res + (float) half));
+    unsigned short z = (unsigned short) clip((int) ((sz - blz) / res + (float) half));
+    float cpx = sx, cpy = sy, cpz = sz;
+    const int x0 = (int) (sx / res), y0 = (int) (sy / res), z0 = (int) (sz / res);
+    const int x1 = (int) (ex / res), y1 = (int) (ey / res), z1 = (int) (ez / res);
+    int dx = abs(x1 - x0), dy = abs(y1 - y0), dz = abs(z1 - z0);
+    int n = 1 + dx + dy + dz;
+    const int x_inc = x1 > x0 ? 1 : (x1 == x0 ? 0 : -1), y_inc = y1 > y0 ? 1 : (y1 == y0 ? 0 : -1),
+              z_inc = z1 > z0 ? 1 : (z1 == z0 ? 0 : -1);
+    int xy_error = dx - dy, xz_error = dx - dz, yz_error = dy - dz;
+    dx *= 2; dy *= 2; dz *= 2;
+    while (n > 0 && steps < (int) max_steps) {
+        // index_map[x + y lim + z lim^2]: the finest node whose index interleaves the cell's bits (bgkblock.cpp:34-67)
+        int idx = 0;
+        for (int l = P.depth - 2; l >= 0; --l)
+            idx = (idx << 3) | (((x >> l) & 1) << 2) | (((y >> l) & 1) << 1) | ((z >> l) & 1);
+        const int node = P.layer_off[P.depth - 1] + idx;
+        la3dm_leaf L;
+        if (slot >= 0) {
+            const unsigned char *rec = pool + (size_t) slot * P.rec_bytes;
+            L = make_leaf(P, key, P.depth - 1, idx, reinterpret_cast<const float2 *>(rec)[node], rec[P.st_off + node],
+                          lut[node], bcx, bcy, bcz);
+            cpx = L.x; cpy = L.y; cpz = L.z;                      // current_p = block->get_point(x, y, z)
+        } else {
+            L = make_leaf(P, key, P.depth - 1, idx, make_float2(P.def_a, P.def_b), (unsigned char) LA3DM_UNKNOWN,
+                          make_float3(0.f, 0.f, 0.f), 0.f, 0.f, 0.f);
+            L.depth = -1;
+            L.x = cpx; L.y = cpy; L.z = cpz;
+        }
+        o[steps++] = L;
+        auto cross = [&](float &bl, int inc, unsigned short &c) {
+            bl += (float) inc * bs;
+            key = make_key(axis_index(blx, bs), axis_index(bly, bs), axis_index(blz, bs));
+            slot = hash_find(hkeys, hvals, mask, key);
+            bcx = axis_center(key >> 40, bs); bcy = axis_center((key >> 20) & 0xFFFFF, bs); bcz = axis_center(key & 0xFFFFF, bs);
+            c = inc > 0 ? 0 : (unsigned short) (lim - 1);
+        };
+        if (xy_error > 0 && xz_error > 0) {
+            x = (unsigned short) (x + x_inc); cpx += (float) x_inc * res; xy_error -= dy; xz_error -= dz;
+            if (x >= lim) cross(blx, x_inc, x);
+        } else if (xy_error < 0 && yz_error > 0) {
+            y = (unsigned short) (y + y_inc); cpy += (float) y_inc * res; xy_error += dx; yz_error -= dz;
+            if (y >= lim) cross(bly, y_inc, y);
+        } else if (yz_error < 0 && xz_error < 0) {
+            z = (unsigned short) (z + z_inc); cpz += (float) z_inc * res; xz_error += dx; yz_error += dy;
+            if (z >= lim) cross(blz, z_inc, z);
+        } else if (xy_error == 0) {
+            x = (unsigned short) (x + x_inc); y = (unsigned short) (y + y_inc);
+            n -= 2;
+            cpx += (float) x_inc * res; cpy += (float) y_inc * res;
+            if (x >= lim) cross(blx, x_inc, x);
+            if (y >= lim) cross(bly, y_inc, y);
+        }
+        --n;
+    }
+    n_steps[r] = steps;
+}
+
 // nodes in the reference's Occupancy layout -> block records; one thread per node, the block's first thread also fills
 // the spare bytes behind the states (leaf count read by k_predict_bgk's early-out, zero padding)
 __global__ void k_unpack_nodes(const la3dm_node *__restrict__ in, unsigned int n_blocks, const DevParams *__restrict__ Pg,
@@ -134,6 +221,25 @@ void Map::search(const float *xyz, size_t n, size_t stride_bytes, bool device_pt
         d_q, (unsigned int) n, (int) (stride_bytes / 4), hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1,
         pool.as<unsigned char>(), d_lut, d_params, finest_only, leaf_out.as<la3dm_leaf>());
     LA3DM_CUDA(cudaMemcpyAsync(out, leaf_out.p, n * sizeof(la3dm_leaf), cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Map::raycast(const float *start_end, size_t n_rays, size_t max_steps, la3dm_leaf *out, int32_t *n_steps) {
+    if (n_rays == 0) return;
+    if (!start_end || !out || !n_steps || max_steps == 0) throw StatusError{LA3DM_ERR_INVALID, "raycast: null argument"};
+    if (n_rays > 0x7FFFFFF0ull || n_rays * max_steps > 0x7FFFFFF0ull) throw StatusError{LA3DM_ERR_INVALID, "raycast: too many steps"};
+    check_synced();
+    LA3DM_CUDA(cudaSetDevice(device));
+    export_tmp.reserve(n_rays * 6 * sizeof(float) + n_rays * sizeof(int32_t), stream);
+    float *d_se = export_tmp.as<float>();
+    int *d_n = reinterpret_cast<int *>(d_se + n_rays * 6);
+    LA3DM_CUDA(cudaMemcpyAsync(d_se, start_end, n_rays * 6 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    leaf_out.reserve(n_rays * max_steps * sizeof(la3dm_leaf), stream);
+    k_raycast<<<ceil_div((long long) n_rays, 128), 128, 0, stream>>>(
+        d_se, (unsigned int) n_rays, (unsigned int) max_steps, hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1,
+        pool.as<unsigned char>(), d_lut, d_params, leaf_out.as<la3dm_leaf>(), d_n);
+    LA3DM_CUDA(cudaMemcpyAsync(n_steps, d_n, n_rays * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaMemcpyAsync(out, leaf_out.p, n_rays * max_steps * sizeof(la3dm_leaf), cudaMemcpyDeviceToHost, stream));
     LA3DM_CUDA(cudaStreamSynchronize(stream));
 }
 

@@ -72,6 +72,19 @@ class _OctoMapBase:
         self._check(self._lib.la3dm_insert_pointcloud(self._h, a.ctypes.data, a.shape[0], a.strides[0], o.ctypes.data,
                                                       float(ds_resolution), float(free_res), float(max_range)))
 
+    def insert_pointcloud_ingest(self, cloud, tf, prefilter_ds, origin, ds_resolution, free_res=2.0, max_range=-1.0,
+                                 min_points=5):
+        """cloudHandler's cloud path (bgkoctomap_server.cpp:70-86): sensor-frame cloud [n, >=3] float32, tf = 3x4 (or 4x4)
+        row-major map <- sensor transform, VoxelGrid prefilter at prefilter_ds (<= 0: none), insert if > min_points."""
+        a = np.asarray(cloud)
+        if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or a.strides[1] != 4 or a.strides[0] % 4:
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(np.asarray(tf, np.float32).reshape(-1)[:12])
+        o = np.ascontiguousarray(origin, dtype=np.float32)
+        self._check(self._lib.la3dm_insert_pointcloud_ingest(
+            self._h, a.ctypes.data, a.shape[0], a.strides[0], t.ctypes.data, float(prefilter_ds), int(min_points),
+            o.ctypes.data, float(ds_resolution), float(free_res), float(max_range)))
+
     def insert_training_data(self, xyzy):
         """insert_training_data(xy): [n, 4] float32 host array of pre-labelled points (x y z label); BGK / GP only."""
         a = np.ascontiguousarray(xyzy, dtype=np.float32).reshape(-1, 4)
@@ -163,6 +176,18 @@ class _OctoMapBase:
             self._check(self._lib.la3dm_search(self._h, q.ctypes.data, len(q), 12, 1 if finest_only else 0,
                                                out.ctypes.data))
         return out
+
+    def raycast(self, starts, ends, max_steps=512):
+        """RayCaster(map, start, end) for a batch of rays -> (steps [n_rays, max_steps] LEAF_DTYPE, n_steps [n_rays]);
+        a step outside any block has depth == -1."""
+        se = np.ascontiguousarray(np.concatenate([np.asarray(starts, np.float32).reshape(-1, 3),
+                                                  np.asarray(ends, np.float32).reshape(-1, 3)], 1))
+        out = np.zeros((len(se), max_steps), LEAF_DTYPE)
+        n = np.zeros(len(se), np.int32)
+        if len(se):
+            self._check(self._lib.la3dm_raycast(self._h, se.ctypes.data, len(se), int(max_steps), out.ctypes.data,
+                                                n.ctypes.data))
+        return out, n
 
     def import_blocks(self, keys, nodes):
         """Inverse of blocks(): fills an empty map from (keys [B], nodes [B, nodes_per_block])."""

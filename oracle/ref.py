@@ -68,6 +68,8 @@ class RefMap:
         L.ref_dump_leaves.argtypes = [C.c_void_p] * 9
         L.ref_get_bbox.argtypes = [C.c_void_p] * 3
         L.ref_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_raycast.restype = C.c_int64
+        L.ref_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6
         L.ref_training_data.restype = C.c_int64
         L.ref_training_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                                         C.c_float, C.c_void_p]
@@ -138,6 +140,17 @@ class RefMap:
         cl = np.zeros(len(q), np.uint8)
         self.lib.ref_search(self.h, q.ctypes.data, len(q), ab.ctypes.data, st.ctypes.data, cl.ctypes.data)
         return ab, st, cl
+
+    def raycast(self, start, end, max_steps=512):
+        """RayCaster(map, start, end): dict of per-step arrays (p [n,3], block_key, node_key, valid, ab [n,2], state)."""
+        a, b = np.ascontiguousarray(start, np.float32), np.ascontiguousarray(end, np.float32)
+        p = np.zeros((max_steps, 3), np.float32)
+        bk, nk = np.zeros(max_steps, np.int64), np.zeros(max_steps, np.int64)
+        ok, st = np.zeros(max_steps, np.uint8), np.zeros(max_steps, np.uint8)
+        ab = np.zeros((max_steps, 2), np.float32)
+        n = int(self.lib.ref_raycast(self.h, a.ctypes.data, b.ctypes.data, max_steps, p.ctypes.data, bk.ctypes.data,
+                                     nk.ctypes.data, ok.ctypes.data, ab.ctypes.data, st.ctypes.data))
+        return dict(p=p[:n], block_key=bk[:n], node_key=nk[:n], valid=ok[:n], ab=ab[:n], state=st[:n])
 
     def get_bbox(self):
         mn = np.zeros(3, np.float32)

@@ -185,6 +185,34 @@ void ref_search(void *h, const float *xyz, int64_t n, float *ab, uint8_t *state,
     }
 }
 
+// RayCaster(map, start, end) walked to its end (at most max_steps): per step the point, block key, node key
+// (depth << 16 | index; LV: << 28), valid flag and the node's two floats / state.  Returns the number of steps.
+int64_t ref_raycast(void *h, const float *start, const float *end, int64_t max_steps, float *p_out, int64_t *block_key,
+                    int64_t *node_key, uint8_t *valid, float *ab, uint8_t *state) {
+    MapT *m = static_cast<MapT *>(h);
+    MapT::RayCaster rc(m, point3f(start[0], start[1], start[2]), point3f(end[0], end[1], end[2]));
+    int64_t i = 0;
+    while (!rc.end() && i < max_steps) {
+        point3f p;
+        la3dm::OcTreeNode node;
+        la3dm::BlockHashKey bk;
+        la3dm::OcTreeHashKey nk;
+        const bool ok = rc.next(p, node, bk, nk);
+        p_out[3 * i] = p.x(); p_out[3 * i + 1] = p.y(); p_out[3 * i + 2] = p.z();
+        block_key[i] = (int64_t) bk;
+        node_key[i] = (int64_t) nk;
+        valid[i] = ok ? 1 : 0;
+#if defined(REF_GP)
+        ab[2 * i] = node.m_ivar; ab[2 * i + 1] = node.ivar;
+#else
+        ab[2 * i] = node.m_A; ab[2 * i + 1] = node.m_B;
+#endif
+        state[i] = (uint8_t) node.get_state();
+        ++i;
+    }
+    return i;
+}
+
 void ref_get_bbox(void *h, float *mn, float *mx) {
     point3f a, b;
     static_cast<MapT *>(h)->get_bbox(a, b);

@@ -65,7 +65,7 @@ def lv_compare(got, want, what):
     rel = err / np.maximum(np.abs(pw), 1e-30)
     ok = err <= 1e-4 * np.abs(pw) + 1e-6
     assert ok.all(), (what, float(err[~ok].max()), int(np.argmax(~ok)), got[int(np.argmax(~ok))], want[int(np.argmax(~ok))])
-    np.testing.assert_allclose(np.stack([got["a"], got["b"]], 1), np.stack([want["a"], want["b"]], 1), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(np.stack([got["a"], got["b"]], 1), np.stack([want["a"], want["b"]], 1), rtol=1e-4, atol=1e-6)
     bad = got["state"] != want["state"]
     near = np.zeros(len(pw), bool)
     for t in (0.3, 0.7):

@@ -176,3 +176,61 @@ def test_search_agrees_with_the_reference_at_depth_4(scans):
     abf, stf, _ = r.search(far)
     gf = m.search(far, finest_only=True)
     assert gf["depth"][0] == -1 and gf["state"][0] == stf[0] == 2 and gf["a"][0] == abf[0, 0] and gf["b"][0] == abf[0, 1]
+
+
+def test_raycast_agrees_with_the_reference_at_depth_4(scans):
+    """BGKOctoMap::RayCaster (bgkoctomap.h:91-214) against the compiled reference at block_depth 4 (where upstream's
+    `lim` and the frozen Block::cell_num agree): the same number of steps, and step by step the same point, block key,
+    finest node, validity and node state; rays inside the map, leaving it, through unknown space, axis-aligned, with
+    xy ties, and a ray whose start block does not exist."""
+    from oracle import ref
+    if not ref.available("bgk"):
+        pytest.skip("oracle/_ref not built")
+    pts, org = scans["sim_structured"]
+    p = dict(ref.DEFAULT_PARAMS["bgk"])
+    p["block_depth"] = 4
+    m, r = new_map("bgk", block_depth=4), ref.RefMap("bgk", p)
+    for i in range(3):
+        m.insert_pointcloud(pts[i], org[i], RES, FREE_RES["bgk"], MAX_RANGE)
+        r.insert_pointcloud(pts[i], org[i], RES, FREE_RES["bgk"], MAX_RANGE)
+    rng = np.random.default_rng(3)
+    o = org[0].astype(np.float32)
+    ends = (o + rng.normal(size=(300, 3)) * np.float32([4, 4, 1])).astype(np.float32)
+    starts = np.tile(o, (len(ends), 1)) + rng.normal(scale=0.3, size=(len(ends), 3)).astype(np.float32)
+    extra_s = np.float32([[o[0], o[1], o[2]], [o[0], o[1], o[2]], [o[0] + 0.33, o[1] - 0.2, o[2]], [300, 300, 300],
+                          [o[0], o[1], o[2]]])
+    extra_e = np.float32([[o[0] + 3.05, o[1], o[2]], [o[0] + 2.0, o[1] + 2.0, o[2]], [o[0] - 2.5, o[1] + 2.5, o[2] + 0.4],
+                          [301, 300, 300], [o[0] + 40.0, o[1] + 1.0, o[2] + 0.3]])
+    starts, ends = np.concatenate([starts, extra_s]).astype(np.float32), np.concatenate([ends, extra_e]).astype(np.float32)
+    steps, n = m.raycast(starts, ends, max_steps=600)
+    total_valid = 0
+    for k in range(len(starts)):
+        w = r.raycast(starts[k], ends[k], max_steps=600)
+        assert n[k] == len(w["valid"]), (k, n[k], len(w["valid"]))
+        g = steps[k, :n[k]]
+        assert np.array_equal(g["depth"] >= 0, w["valid"] == 1), k
+        assert np.array_equal(g["block_key"], w["block_key"]), k
+        assert np.array_equal((3 << 16) + g["index"], w["node_key"]), k           # node key = (depth << 16) + index
+        assert np.array_equal(np.stack([g["x"], g["y"], g["z"]], 1), w["p"]), k
+        v = w["valid"] == 1
+        assert np.array_equal(g["state"][v], w["state"][v]), k
+        np.testing.assert_allclose(g["a"][v], w["ab"][v, 0], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(g["b"][v], w["ab"][v, 1], rtol=1e-4, atol=1e-6)
+        total_valid += int(v.sum())
+    assert total_valid > 5000 and n[-2] == 0 and (steps[-1, :n[-1]]["depth"] == -1).any()
+
+
+def test_raycast_depth_3_is_consistent_with_search(scans):
+    """block_depth 3 (the reference configuration; upstream's RayCaster mixes 2^(depth-1) with cell_num = 8 there):
+    every valid step is the finest node la3dm_search(finest_only) returns for the step's own point."""
+    m = build(scans, n=3)
+    o = scans["sim_structured"][1][0]
+    rng = np.random.default_rng(5)
+    ends = (o + rng.normal(size=(64, 3)) * np.float32([3, 3, 1])).astype(np.float32)
+    steps, n = m.raycast(np.tile(o, (64, 1)), ends, max_steps=400)
+    assert (n > 0).all()
+    for k in range(64):
+        g = steps[k, :n[k]]
+        g = g[g["depth"] >= 0]
+        s = m.search(np.stack([g["x"], g["y"], g["z"]], 1), finest_only=True)
+        assert s.tobytes() == g.tobytes()
