@@ -370,7 +370,8 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
        const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
        const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask, long long *keys,
        NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list, unsigned int *light_list,
-       uint4 *mega_list, unsigned int *chunk_mega, unsigned char *dirty, const unsigned int *__restrict__ tile_sums,
+       uint4 *mega_list, unsigned int *chunk_mega, unsigned char *dirty, unsigned int *cell_test,
+       const unsigned int *__restrict__ tile_sums,
        unsigned int n_tiles, int prescanned, unsigned char *pool, const DevParams *__restrict__ P, int init_records) {
     __shared__ unsigned int smem[66];
     if (c->overflow) return;
@@ -438,6 +439,7 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
         }
     }
     if (!valid) return;
+    if (cell_test) cell_test[test_id[t]] = t + 1;
     const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
     unsigned int tot = 0;
     const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
@@ -547,6 +549,7 @@ void Map::enqueue_binning() {
     // (the bounding box mm was accumulated by the front-end kernels that wrote xy)
     enqueue_block_grid();
     LA3DM_CUDA(cudaMemsetAsync(cell_db.p, 0, (size_t) caps.cells * 4, stream));
+    if (hp.method == LA3DM_GP) LA3DM_CUDA(cudaMemsetAsync(cell_test.p, 0, (size_t) caps.cells * 4, stream));
     const unsigned int n_words = (caps.cells + 31) / 32;
     LA3DM_CUDA(cudaMemsetAsync(test_bits.p, 0, (size_t) n_words * 4, stream));
 
@@ -595,7 +598,8 @@ void Map::enqueue_binning() {
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
         hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr,
         hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr, light_list.as<unsigned int>(),
-        mega_list.as<uint4>(), chunk_mega.as<unsigned int>(), dirty.as<unsigned char>(), tile_sums, (unsigned int) p_tiles,
+        mega_list.as<uint4>(), chunk_mega.as<unsigned int>(), dirty.as<unsigned char>(),
+        hp.method == LA3DM_GP ? cell_test.as<unsigned int>() : nullptr, tile_sums, (unsigned int) p_tiles,
         p_prescanned, pool.as<unsigned char>(), d_params, hp.method == LA3DM_BGK ? 1 : 0);
     ++launches;
     launches += 3;

@@ -326,6 +326,7 @@ void Map::ensure_workspace() {
         moved |= gp_mv.reserve(std::min<size_t>(caps.tests, chunk) * 7 * groups * 32 * 8, stream);
     }
     if (hp.method == LA3DM_GP) {
+        moved |= cell_test.reserve((size_t) caps.cells * 4, stream);
         moved |= gp_sizes.reserve(((size_t) caps.members + 2) * 8, stream);
         moved |= gp_off.reserve(((size_t) caps.members + 2) * 8, stream);
         moved |= gp_store.reserve((size_t) caps.gp_store * 4, stream);

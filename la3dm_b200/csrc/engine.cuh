@@ -49,6 +49,7 @@ struct Map {
     DevBuf pts_sorted;              // float4 block-sorted, pre-scaled for the method's kernel
     DevBuf db_id, db_start;         // data blocks: dense cell id, start (+ sentinel)
     DevBuf cell_db, test_bits;      // dense per-cell arrays of the scan's block grid
+    DevBuf cell_test;               // GP: cell -> test block index + 1 (predict_gp_tc.cu walks data blocks)
     DevBuf test_id, plan, heavy_list, light_list, mega_list, chunk_mega, mega_acc;
     DevBuf gp_sizes, gp_off, gp_store, gp_scratch, gp_mv, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
@@ -123,6 +124,7 @@ struct Map {
     void enqueue_predict();
     void enqueue_gp();
     void enqueue_gp_sizes();
+    void enqueue_gp_mv_tc(unsigned int t0, unsigned int chunk);
     void enqueue_peer_wait();
     void peer_sync();
     void check_synced() const;

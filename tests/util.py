@@ -67,3 +67,23 @@ def compare_leaves(got, want, prob_rtol=PROB_RTOL, thresholds=(0.3, 0.7), what="
     cls_bad = int((got["classified"] != want["classified"]).sum())
     assert cls_bad <= max(2, len(want) // 5000), "%s classified mismatches: %d" % (what, cls_bad)
     return dict(max_rel=float(rel.max()) if len(rel) else 0.0, state_mismatch=int(bad.sum()), classified_mismatch=cls_bad)
+
+
+def gp_compare(got, want, what="", p99=1e-4, pmax=2e-2):
+    """GPOctoMap parity gate.  K + noise I has cond ~ 1e4 in fp32 and var = sf2 - |L^-1 k|^2 cancels to ~1e-3 before it
+    enters as 1 / var, so two fp32 evaluations of the same algorithm that add in a different order (the reference's
+    R-tree order, the CPU restatement's array order, the tensor-core blocked TRSM) agree in PROBABILITY to p99 < 1e-4 and
+    a few 1e-3 at worst (profiles/r2_parity_gp_vs_ref.json) -- a relative bound is meaningless for p ~ 1e-29.  Leaf sets,
+    centres and sizes stay bit-exact; states may differ only where the probability sits on a threshold."""
+    assert len(got) == len(want), "%s leaf count %d != %d" % (what, len(got), len(want))
+    for k in ("block_key", "depth", "index", "x", "y", "z", "size"):
+        assert np.array_equal(got[k], want[k]), "%s leaf %s differ" % (what, k)
+    err = np.abs(got["prob"].astype(np.float64) - want["prob"].astype(np.float64))
+    q99, worst = (float(np.percentile(err, 99)), float(err.max())) if len(err) else (0.0, 0.0)
+    assert q99 <= p99 and worst <= pmax, "%s |dp| p99 %.2e max %.2e" % (what, q99, worst)
+    bad = got["state"] != want["state"]
+    pw = want["prob"].astype(np.float64)
+    near = (np.abs(pw - 0.3) <= 5e-3) | (np.abs(pw - 0.7) <= 5e-3) | (want["state"] == 2) | (got["state"] == 2)
+    assert not (bad & ~near).any(), "%s %d state mismatches away from thresholds" % (what, int((bad & ~near).sum()))
+    assert np.array_equal(got["classified"], want["classified"]), what
+    return dict(p99=q99, max=worst, state_mismatch=int(bad.sum()))
