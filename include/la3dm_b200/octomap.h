@@ -104,6 +104,41 @@ public:
         dirty_ = true;
     }
 
+    /// insert_training_data (include/bgkoctomap/bgkoctomap.h:86; BGKOctoMap and GPOctoMap): GPPointCloud is
+    /// std::vector<std::pair<point3f, float>> upstream -- any container of pairs (point with x() y() z(), label) works
+    template <class GPPointCloud>
+    void insert_training_data(const GPPointCloud &xy) {
+        std::vector<float> buf;
+        buf.reserve(4 * xy.size());
+        for (auto it = xy.begin(); it != xy.end(); ++it) {
+            buf.push_back(it->first.x()); buf.push_back(it->first.y()); buf.push_back(it->first.z());
+            buf.push_back(it->second);
+        }
+        check(la3dm_insert_training_data(h_, buf.data(), buf.size() / 4, 16));
+        dirty_ = true;
+    }
+
+    /// cloudHandler's cloud path (src/bgkoctomap/bgkoctomap_server.cpp:70-86) in one call: sensor-frame cloud, the
+    /// map <- sensor transform as 3 x 4 row-major floats, VoxelGrid prefilter, insert if more than min_points are left
+    template <class Cloud, class Point>
+    void insert_pointcloud_ingest(const Cloud &cloud, const float tf[12], float prefilter_ds, const Point &origin,
+                                  float ds_resolution, float free_res = 2.0f, float max_range = -1, int min_points = 5) {
+        const float o[3] = {origin.x(), origin.y(), origin.z()};
+        const size_t n = cloud.points.size();
+        const float *xyz = n ? reinterpret_cast<const float *>(&cloud.points[0]) : nullptr;
+        check(la3dm_insert_pointcloud_ingest(h_, xyz, n, sizeof(cloud.points[0]), tf, prefilter_ds, min_points, o,
+                                             ds_resolution, free_res, max_range));
+        dirty_ = true;
+    }
+
+    /// multi-GPU replicas (include/la3dm_b200.h, "multi-GPU, BGKOctoMap"); one map object per GPU
+    void reserve_blocks(size_t n) { check(la3dm_reserve_blocks(h_, n)); }
+    void peer_set_deferred(bool on) { check(la3dm_peer_set_deferred(h_, on ? 1 : 0)); }
+    void peer_attach(int world, int rank, void *const *pool_bases, void *const *flags) {
+        check(la3dm_peer_attach(h_, world, rank, pool_bases, flags));
+    }
+    void peer_sync() { check(la3dm_peer_sync(h_)); dirty_ = true; }
+
     /// get_bbox (src/bgkoctomap/bgkoctomap.cpp:368-381)
     template <class Point>
     void get_bbox(Point &lim_min, Point &lim_max) const {
@@ -167,6 +202,35 @@ public:
     void search(const float *xyz, size_t n, size_t stride_bytes, la3dm_leaf *out, bool finest_only = false) const {
         check(la3dm_search(h_, xyz, n, stride_bytes, finest_only ? 1 : 0, out));
     }
+    /// RayCaster (include/bgkoctomap/bgkoctomap.h:91-214): `RayCaster ray(&map, start, end); while (!ray.end()) {
+    /// if (ray.next(p, node, block_key, node_key)) ... }` -- the whole walk is done on the device at construction
+    /// (la3dm_raycast), next() hands its steps out one by one.  node_key = (depth << 16) + index like OcTreeHashKey.
+    class RayCaster {
+    public:
+        template <class Point>
+        RayCaster(const OctoMapT *map, const Point &start, const Point &end, size_t max_steps = 4096) : i_(0) {
+            const float se[6] = {start.x(), start.y(), start.z(), end.x(), end.y(), end.z()};
+            steps_.resize(max_steps);
+            int32_t n = 0;
+            map->check(la3dm_raycast(map->h_, se, 1, max_steps, steps_.data(), &n));
+            steps_.resize((size_t) n);
+        }
+        bool end() const { return i_ >= steps_.size(); }
+        template <class Point>
+        bool next(Point &p, OcTreeNode &node, BlockHashKey &block_key, uint32_t &node_key) {
+            const la3dm_leaf &l = steps_[i_++];
+            p = Point(l.x, l.y, l.z);
+            block_key = l.block_key;
+            const bool valid = l.depth >= 0;
+            node_key = (uint32_t) ((valid ? l.depth : 0) << 16) + (uint32_t) l.index;
+            if (valid) node = OcTreeNode(l);
+            return valid;
+        }
+    private:
+        std::vector<la3dm_leaf> steps_;
+        size_t i_;
+    };
+
     /// checkpoint / resume (la3dm_save / la3dm_load; load needs an empty map with the same parameters)
     void save(const std::string &path) const { check(la3dm_save(h_, path.c_str())); }
     void load(const std::string &path) { check(la3dm_load(h_, path.c_str())); dirty_ = true; }

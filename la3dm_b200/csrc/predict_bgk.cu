@@ -48,7 +48,8 @@ __device__ __forceinline__ unsigned char bgk_update(float &a, float &b, float yb
     return bgk_classify(a, b, P);
 }
 
-// ---- block_depth 4: 512 finest voxels per block, 16 slots per lane, record updated in global memory ----------------
+// ---- block_depth >= 4: 512 finest voxels per pass (16 slots per lane), as many passes as the block needs (1 at depth
+// 4, 8 at depth 5, 64 at depth 6); the record is updated in global memory, neighbour after neighbour like upstream ------
 constexpr int kDeepSlots = 16;
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -70,6 +71,7 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     const int D = P.depth, finest = P.finest;
     const float ell = P.ell, sf2 = P.sf2;
     const int shard_world = A->shard_world, shard_rank = A->shard_rank;
+    const bool no_guard = A->training_data != 0;        // insert_training_data: bgkoctomap.cpp:179 has no kbar guard
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
     // test block t belongs to rank t % world: this rank walks t = u * world + rank, u dealt over its warps
@@ -87,12 +89,13 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
         const long long key = keys[pl.slot];
         const float cx = axis_center(key >> 40, P.block_size), cy = axis_center((key >> 20) & 0xFFFFF, P.block_size),
                     cz = axis_center(key & 0xFFFFF, P.block_size);
+        for (int pass0 = 0; pass0 < finest; pass0 += 32 * kDeepSlots) {
         int node[kDeepSlots];
         float px[kDeepSlots], py[kDeepSlots], pz[kDeepSlots], a[kDeepSlots], b[kDeepSlots];
         unsigned char state[kDeepSlots], touched[kDeepSlots];
 #pragma unroll
         for (int s = 0; s < kDeepSlots; ++s) {
-            const int j = lane + 32 * s;
+            const int j = pass0 + lane + 32 * s;
             node[s] = -1;
             touched[s] = 0;
             state[s] = LA3DM_UNKNOWN;
@@ -144,7 +147,7 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             for (int s = 0; s < kDeepSlots; ++s) {
                 if (node[s] >= 0) {
                     pairs += cntp;
-                    if (kb[s] > 0.0f) {
+                    if (kb[s] > 0.0f || no_guard) {
                         state[s] = bgk_update(a[s], b[s], yb[s], kb[s], U) | 0x80;
                         touched[s] = 1;
                     }
@@ -159,6 +162,7 @@ k_predict_bgk_deep(const NeighbourPlan *__restrict__ plan, const float4 *__restr
                 ++updates;
             }
         }
+        }   // passes
         __syncwarp();
         for (int d = D - 1; d > 0; --d) {
             const int off = P.layer_off[d], poff = P.layer_off[d - 1];
@@ -682,11 +686,10 @@ void Map::enqueue_predict() {
 #undef LA3DM_FLAT_ARGS
         launches += 2;
     }
-    else if (hp.depth == 4)
+    else
         k_predict_bgk_deep<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), pts_sorted.as<float4>(),
                                                                    keys.as<long long>(), pool.as<unsigned char>(),
                                                                    d_lut, d_params, d_args, d_cnt);
-    else throw StatusError{LA3DM_ERR_UNSUPPORTED, "block_depth > 4 not supported by the BGK kernel yet"};
     record_event(ev_p1);
     ++launches;
 }

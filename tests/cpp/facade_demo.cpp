@@ -1,9 +1,10 @@
 // Test program for the C++ facade (include/la3dm_b200/octomap.h): reads like the reference's static node
 // (src/bgkoctomap/bgkoctomap_static_node.cpp:86-139): construct, insert scans, walk the leaves.
 // usage: facade_demo <scan file: int32 n_scans, int32 n_pts, float origins[n_scans][3], float pts[n_scans][n_pts][3]>
-// prints: leaves free occupied unknown sum_prob bbox(6)
+// prints: leaves free occupied unknown sum_prob bbox(6) probe_prob ray_steps ray_valid ray_bad
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "la3dm_b200/octomap.h"
@@ -42,10 +43,41 @@ int main(int argc, char **argv) {
         else ++nu;
         sp += node.get_prob();
     }
+    // RayCaster like the (commented-out) use in src/bgkloctomap/bgkloctomap_static_node.cpp:117-129: walk a ray from the
+    // first sensor origin; every valid step must be the node search() names for the step's own point
+    long ray_steps = 0, ray_valid = 0, ray_bad = 0;
+    {
+        la3dm::vec3f start(org[0], org[1], org[2]), end(org[0] + 3.0f, org[1] + 1.0f, org[2] + 0.2f);
+        la3dm::BGKOctoMap::RayCaster ray(&map, start, end);
+        while (!ray.end()) {
+            la3dm::vec3f p;
+            la3dm::OcTreeNode node;
+            la3dm::BlockHashKey bk;
+            uint32_t nk;
+            ++ray_steps;
+            if (ray.next(p, node, bk, nk)) {
+                ++ray_valid;
+                la3dm_leaf l;
+                const float q[3] = {p.x(), p.y(), p.z()};
+                map.search(q, 1, sizeof(q), &l, true);
+                if (l.block_key != bk || ((uint32_t) (l.depth << 16) + (uint32_t) l.index) != nk || l.a != node.get_a()) ++ray_bad;
+            }
+        }
+    }
+    // insert_training_data: three labelled points next to the first origin
+    {
+        std::vector<std::pair<la3dm::vec3f, float>> xy;
+        xy.emplace_back(la3dm::vec3f(org[0] + 0.5f, org[1], org[2]), 1.0f);
+        xy.emplace_back(la3dm::vec3f(org[0] + 0.3f, org[1], org[2]), 0.0f);
+        xy.emplace_back(la3dm::vec3f(org[0] + 0.1f, org[1], org[2]), 0.0f);
+        la3dm::BGKOctoMap side(0.1f, 3, 1.0f, 0.2f, 0.3f, 0.7f, 100.0f, 0.001f, 0.001f);
+        side.insert_training_data(xy);
+        if (side.num_blocks() == 0 || side.search(org[0] + 0.5f, org[1], org[2]).get_prob() <= 0.9f) ++ray_bad;
+    }
     la3dm::vec3f mn, mx;
     map.get_bbox(mn, mx);
     const la3dm::OcTreeNode probe = map.search(5.05f, 0.15f, 1.35f);    // SURVEY.md 8c known answer after scan 1
-    printf("%ld %ld %ld %ld %.4f %.9g %.9g %.9g %.9g %.9g %.9g %.7f\n", n, nf, no, nu, sp, mn.x(), mn.y(), mn.z(), mx.x(),
-           mx.y(), mx.z(), probe.get_prob());
+    printf("%ld %ld %ld %ld %.4f %.9g %.9g %.9g %.9g %.9g %.9g %.7f %ld %ld %ld\n", n, nf, no, nu, sp, mn.x(), mn.y(), mn.z(),
+           mx.x(), mx.y(), mx.z(), probe.get_prob(), ray_steps, ray_valid, ray_bad);
     return 0;
 }

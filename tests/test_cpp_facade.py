@@ -41,3 +41,4 @@ def test_facade_matches_golden_sequence(tmp_path, scans):
     assert got[:4] == list(want[:4])                      # leaves, FREE, OCCUPIED, UNKNOWN
     assert abs(got[4] - want[6]) <= 1e-4 * want[6]        # sum of probabilities
     assert 0.0 < got[11] < 1.0
+    assert got[12] >= got[13] > 10 and got[14] == 0     # RayCaster steps, valid steps, inconsistencies
