@@ -190,7 +190,8 @@ struct Caps {
 
 enum : unsigned int {
     OVF_RAW = 1u, OVF_MEMBERS = 2u, OVF_CELLS = 4u, OVF_TESTS = 8u, OVF_EXTENT = 16u, OVF_POOL = 32u, OVF_VGCELLS = 64u,
-    OVF_GPSTORE = 128u, OVF_GPN = 256u, OVF_LVACTIVE = 512u, OVF_PEER = 1024u
+    OVF_GPSTORE = 128u, OVF_GPN = 256u, OVF_LVACTIVE = 512u, OVF_PEER = 1024u,
+    OVF_FAST = 2048u      // a list too long for the sort-free front-end (frontend_fused.cu): replay on the legacy pipeline
 };
 
 // counters the host reads back once per scan (pinned mirror)
@@ -221,6 +222,9 @@ struct ScanCounters {
     unsigned int n_heavy;        // test blocks with more than kHeavyTot training points in their ExtendedBlock
     unsigned int ctas_done;      // CTAs of the predict kernel that have pushed everything to the peers
     unsigned long long gp_store_needed;
+    unsigned int n_extra;        // fused binning: memberships beyond an entry's first
+    unsigned int _pad_extra;
+    unsigned int fz_nlong[3][2]; // fused front-end: spans longer than kShortRun ([voxel grid 1, 2, binning][warp, CTA])
 };
 
 #ifndef LA3DM_TILE

@@ -118,6 +118,7 @@ Map::~Map() {
     if (h_cnt) cudaFreeHost(h_cnt);
     if (d_args) cudaFree(d_args);
     if (d_peers) cudaFree(d_peers);
+    if (fz_bar) cudaFree(fz_bar);
     if (h_args) cudaFreeHost(h_args);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -153,6 +154,8 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     LA3DM_CUDA(cudaEventCreateWithFlags(&ev_wait, cudaEventDisableTiming));
     const char *env = getenv("LA3DM_NO_GRAPH");
     use_graph = !(env && env[0] == '1');
+    const char *legacy = getenv("LA3DM_LEGACY_FRONTEND");
+    use_fused = !(legacy && legacy[0] == '1');
 
     api_params = p;
     DevParams &h = hp;
@@ -337,6 +340,7 @@ void Map::ensure_workspace() {
     const size_t tmp = std::max(radix_sort_temp_bytes((unsigned int) n_sort),
                                 hp.method == LA3DM_GP ? scan_temp_bytes(caps.members) : (size_t) 0);
     if (tmp > cub_tmp_bytes) { moved |= cub_tmp.reserve(tmp, stream); cub_tmp_bytes = tmp; }
+    if (hp.method == LA3DM_BGK || hp.method == LA3DM_GP) moved |= ensure_fused_workspace();
     if (moved) invalidate_graph();
 }
 
@@ -402,7 +406,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         LA3DM_CUDA(cudaEventRecord(ev0, stream));
         LA3DM_CUDA(cudaMemcpyAsync(d_args, h_args, sizeof(ScanArgs), cudaMemcpyHostToDevice, stream));
         if (use_graph) {
-            if (!graph_exec || !(graph_caps == caps) || graph_mode != mode) {
+            if (!graph_exec || !(graph_caps == caps) || graph_mode != mode || graph_fused != fused_applicable(mode)) {
                 invalidate_graph();
                 cudaGraph_t g = nullptr;
                 LA3DM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -419,6 +423,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
                 LA3DM_CUDA(e);
                 graph_caps = caps;
                 graph_mode = mode;
+                graph_fused = fused_applicable(mode);
                 graph_launches = launches;
                 ++call_captures;
             }
@@ -439,6 +444,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         ++call_replays;
         if (ovf & OVF_EXTENT) throw StatusError{LA3DM_ERR_EXTENT, "scan bounding box spans too many blocks"};
         if (ovf & OVF_PEER) throw StatusError{LA3DM_ERR_CUDA, "timed out waiting for a peer replica to finish the scan"};
+        if (ovf & OVF_FAST) use_fused = false;   // a list too long for the sort-free front-end: legacy pipeline from here on
         if (ovf & OVF_VGCELLS) {   // only the bit count matters (radix-sort passes): next power of two
             unsigned int v = 1u << 20;
             while (v < h_cnt->vg_cells_needed && v < 0x80000000u) v <<= 1;
@@ -456,6 +462,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         if (caps.members < caps.train / 2) caps.members = caps.train / 2;
     }
 
+    dump_fused_trace();
     if (!frontend_only) { ++scan_seq; if (peers_attached && peers_deferred) peers_unsynced = true; }
     // blocks after the scan = blocks before + blocks k_plan / k_lv_blocks created (no overflow on this path)
     n_blocks = frontend_only ? n_blocks : (long long) h_args->n_blocks + (long long) h_cnt->n_new_blocks;

@@ -55,6 +55,9 @@ struct Map {
     int gp_ctas = 0;
     DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists
     DevBuf lv_range, lv_info, ray_first, lv_qgrid, lv_active, lv_blk_slot, lv_blk_flags;   // BGKLVOctoMap
+    DevBuf fz_vcnt, fz_bits, fz_wpre, fz_cell_cnt, fz_extra, fz_tsum, fz_newsums, fz_bsum, fz_long;   // sort-free front-end (frontend_fused.cu)
+    unsigned int *fz_bar = nullptr;
+    bool use_fused = true;          // LA3DM_LEGACY_FRONTEND=1, or a scan that raised OVF_FAST, switches to frontend.cu / binning.cu
     DevBuf beam_tab;                // sample distances of beam_sample for the current free_resolution
     float beam_tab_fr = 0.f;
     size_t cub_tmp_bytes = 0;
@@ -72,6 +75,7 @@ struct Map {
     cudaGraphExec_t graph_exec = nullptr;
     Caps graph_caps{};
     int graph_mode = -1;
+    bool graph_fused = false;
     int graph_launches = 0;
     bool use_graph = true;
     int replays = 0;                // scans re-run after a capacity overflow (lifetime counter)
@@ -84,6 +88,7 @@ struct Map {
     PeerTable h_peers{};
     PeerTable *d_peers = nullptr;
     DevBuf peer_flags;              // [kMaxPeers] u64, written by the peers
+    bool peers_share_device = false;   // a peer replica lives on this very device (single-GPU tests)
     bool peers_attached = false, peers_deferred = false, peers_unsynced = false;
     DevBuf dirty;                   // [pool_cap] bytes: block changed since the last la3dm_peer_sync (deferred mode)
     unsigned long long sync_seq = 0;
@@ -126,6 +131,11 @@ struct Map {
     void enqueue_gp_sizes();
     void enqueue_gp_mv_tc(unsigned int t0, unsigned int chunk);
     void enqueue_peer_wait();
+    bool ensure_fused_workspace();
+    bool fused_applicable(int mode) const;
+    void enqueue_fused_begin(int reset_counters);
+    void enqueue_fused(int stage);
+    void dump_fused_trace();
     void peer_sync();
     void check_synced() const;
     // export

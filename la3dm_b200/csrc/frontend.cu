@@ -765,17 +765,24 @@ void Map::enqueue_ingest() {
 void Map::enqueue_scan(int mode) {
     const bool frontend_only = mode == 1;
     launches = 0;
-    k_scan_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm);
-    ++launches;
+    // BGK / GP: the sort-free cooperative pipeline (frontend_fused.cu) unless it was switched off
+    const bool fused = fused_applicable(mode);
+    if (fused) enqueue_fused_begin(1);
+    else { k_scan_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm); ++launches; }
     if (mode == 3) enqueue_ingest();
     if (mode == 2) enqueue_training_data();
     else if (hp.method == LA3DM_BGKL) enqueue_frontend_bgkl();
     else if (hp.method == LA3DM_BGKLV) enqueue_frontend_lv();
+    else if (fused) enqueue_fused(0);
     else enqueue_frontend_bgk();
     if (!frontend_only && hp.method == LA3DM_BGKLV) {
         enqueue_lv();
     } else if (!frontend_only) {
-        enqueue_binning();
+        if (fused) {
+            enqueue_fused(1);
+            if (hp.method == LA3DM_GP) enqueue_gp_sizes();   // capacity checks before the plan touches the map
+            enqueue_fused(2);
+        } else enqueue_binning();
         if (hp.method == LA3DM_GP) enqueue_gp();
         else if (hp.method == LA3DM_BGKL) enqueue_predict_bgkl();
         else enqueue_predict();

@@ -247,6 +247,13 @@ int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bas
     cudaStreamSynchronize(m.stream);
     cudaError_t e = cudaMemcpy(m.d_peers, &t, sizeof(t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return peer_fail(map, "peer table upload", e);
+    m.peers_share_device = false;
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, pool_bases[p]) == cudaSuccess) { if (at.device == m.device) m.peers_share_device = true; }
+        else cudaGetLastError();
+    }
     m.shard_rank = rank;
     m.shard_world = world;
     m.peers_attached = true;
