@@ -110,6 +110,7 @@ __device__ __forceinline__ void trace_mark(unsigned long long *trace, unsigned i
 }
 __device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch, unsigned long long *trace = nullptr) {
     __syncthreads();
+    if (gridDim.x == 1 && !trace) return;                   // one CTA: block-level visibility is all that is needed
     if (threadIdx.x == 0) {
         epoch += gridDim.x;
         const unsigned long long t0 = trace ? global_ns() : 0ull;
@@ -585,9 +586,29 @@ __device__ inline unsigned int hit_free_count(const float4 h, const ScanArgs *A)
 template <int W>
 __device__ __forceinline__ void centroid_done(const FusedArgs &F, unsigned int r, float4 v, Box &box) {
     if (W == 0) {
-        const unsigned int cnt = hit_free_count(v, F.A);
+        const ScanArgs *A = F.A;
+        const unsigned int cnt = hit_free_count(v, A);
         F.hit_cnt[r] = cnt;
-        if (cnt) atomicAdd(&F.bsum[r / kBeamTile], (1ull << 32) | (unsigned long long) cnt);
+        if (cnt) {
+            atomicAdd(&F.bsum[r / kBeamTile], (1ull << 32) | (unsigned long long) cnt);
+            // Bounding box of this beam's free points (getMinMax3D of the second voxel grid) without generating them:
+            // every sample is o + n * d, rounded, and rounding is monotonic in d, so on every axis the extremes are at the
+            // origin, the nearest and the farthest sample (same expressions as beam_fill).
+            const float ox = A->ox, oy = A->oy, oz = A->oz, fr = A->fr;
+            const float dx = v.x - ox, dy = v.y - oy, dz = v.z - oz;
+            const float l = (float) sqrt((double) (dx * dx + dy * dy + dz * dz));
+            const float nx = dx / l, ny = dy / l, nz = dz / l;
+            const unsigned int tail = l > fr ? 1u : 0u, n_reg = cnt - 1u - tail;
+            box.add(ox, oy, oz);
+            if (n_reg) {
+                const float d0 = A->beam_tab[0];
+                const unsigned int e = n_reg - 1u;
+                const float d1 = e < A->beam_tab_n ? A->beam_tab[e] : add_repeat(fr, fr, e);
+                box.add(ox + nx * d0, oy + ny * d0, oz + nz * d0);
+                box.add(ox + nx * d1, oy + ny * d1, oz + nz * d1);
+            }
+            if (tail) { const float d = l - fr; box.add(ox + nx * d, oy + ny * d, oz + nz * d); }
+        }
     } else box.add(v.x, v.y, v.z);
 }
 
@@ -622,14 +643,29 @@ __device__ void vg_centroid(const FusedArgs &F, unsigned long long *smem, unsign
             if (W == 1 && r2 == r0) continue;
             const unsigned int run_first = F.vstart[r2], run_last = F.vstart[r2 + 1];
             float acc = 0.f;
+            float px[kMidStage / 32], py[kMidStage / 32], pz[kMidStage / 32];
+            auto fetch = [&](unsigned int s0) {
+                const unsigned int mcount = min((unsigned int) kMidStage, run_last - s0);
+#pragma unroll
+                for (int k = 0; k < kMidStage / 32; ++k) {
+                    const unsigned int j = lane + 32 * k;
+                    if (j < mcount) {
+                        const float *p = V.in + (size_t) F.vsorted[s0 + j] * V.stride;
+                        px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+                    }
+                }
+            };
+            fetch(run_first);
             for (unsigned int s0 = run_first; s0 < run_last; s0 += kMidStage) {
                 const unsigned int mcount = min((unsigned int) kMidStage, run_last - s0);
                 __syncwarp();
-                for (unsigned int j = lane; j < mcount; j += 32) {
-                    const float *p = V.in + (size_t) F.vsorted[s0 + j] * V.stride;
-                    wstage[warp][0][j] = p[0]; wstage[warp][1][j] = p[1]; wstage[warp][2][j] = p[2];
+#pragma unroll
+                for (int k = 0; k < kMidStage / 32; ++k) {
+                    const unsigned int j = lane + 32 * k;
+                    if (j < mcount) { wstage[warp][0][j] = px[k]; wstage[warp][1][j] = py[k]; wstage[warp][2][j] = pz[k]; }
                 }
                 __syncwarp();
+                if (s0 + kMidStage < run_last) fetch(s0 + kMidStage);     // in flight while three lanes add this chunk
                 if (lane < 3) acc = seq_sum(acc, wstage[warp][lane], mcount);
             }
             acc = acc / (float) (run_last - run_first);
@@ -692,7 +728,7 @@ __device__ void vg_centroid(const FusedArgs &F, unsigned long long *smem, unsign
         out[off + r] = v;
         centroid_done<W>(F, r, v, box);
     }
-    if (W == 1) box.flush(F.mm + 12, s_mm);
+    box.flush(F.mm + (W == 1 ? 12 : 6), s_mm);
     if (W == 0 && !V.pass) {
         // second pass starts from a clear bitmap and clear counts
         zero_words(F.bits, min(V.words(), F.bits_words));
@@ -723,9 +759,26 @@ __device__ void beam_fill(const FusedArgs &F, unsigned long long *smem, unsigned
     }
     if (n_raw > F.raw_cap) return;
     const float ox = A->ox, oy = A->oy, oz = A->oz, fr = A->fr;
+    // the second voxel grid's frame is known (bounding box from vg_centroid<0>): cell of every sample, one bit per cell
+    const float inv = A->inv_ds;
+    VGFrame f2;
+    f2.passthrough = true; f2.cells = 0;
+    if (!(A->ds < 0) && n_raw > 0) f2 = vg_frame(F.mm + 6, inv);
+    const bool pass2 = A->ds < 0 || f2.passthrough;
+    const bool cells_ok = (unsigned long long) f2.cells <= (unsigned long long) F.vg_cells_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !dead && n_raw > 0) {
+        c->vg_passthrough[1] = pass2 ? 1u : 0u;
+        if (!pass2 && !cells_ok) {
+            atomicOr(&c->overflow, OVF_VGCELLS);
+            atomicMax(&c->vg_cells_needed, (unsigned int) (f2.cells > 0x80000000ll ? 0x80000000ll : f2.cells));
+        }
+        // the sensor origin's voxel exists whatever else falls into it (the origin copies are not listed)
+        if (!pass2 && cells_ok) set_bit(F.bits, vg_cell(f2, inv, ox, oy, oz));
+    }
+    const bool keys2 = !pass2 && cells_ok;
     const unsigned int tab_n = A->beam_tab_n;
     const float *__restrict__ tab = A->beam_tab;
-    Box sbox, hbox;
+    Box hbox;
     TileCarry<unsigned long long> carry;
     for (unsigned int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const unsigned int i = t * kBeamTile + threadIdx.x;
@@ -751,6 +804,7 @@ __device__ void beam_fill(const FusedArgs &F, unsigned long long *smem, unsigned
         __syncthreads();
         const unsigned int tile_total = (unsigned int) (cta_total & 0xFFFFFFFFull);
         float4 *out = F.frees_raw + (unsigned int) (prefix & 0xFFFFFFFFull);
+        unsigned int *kout = F.vkey + (unsigned int) (prefix & 0xFFFFFFFFull);
         for (unsigned int q = threadIdx.x; q < tile_total; q += kFT) {
             // h = the last hit of the tile whose first free point is at or before q
             unsigned int lo = 0, hi = kBeamTile;
@@ -768,11 +822,14 @@ __device__ void beam_fill(const FusedArgs &F, unsigned long long *smem, unsigned
                 w = (int) s_ord[h];
             }
             out[q] = make_float4(sx, sy, sz, __int_as_float(w));
-            sbox.add(sx, sy, sz);
+            if (keys2) {
+                unsigned int cell = kPad;                                  // (an origin copy stays out of the lists)
+                if (e1) { cell = vg_cell(f2, inv, sx, sy, sz); set_bit(F.bits, cell); }
+                kout[q] = cell;
+            }
         }
         __syncthreads();
     }
-    sbox.flush(F.mm + 6, s_mm);
     hbox.flush(F.mm + 12, s_mm);
 }
 
@@ -1185,7 +1242,7 @@ __device__ void plan_find(const FusedArgs &F) {
 
 // creation of the new blocks in test-block order, the 7 neighbour ranges, this rank's work lists: k_plan (binning.cu).
 // The first phase of the scan that writes to the persistent map; every capacity check has been made by now.
-__device__ void plan_fill(const FusedArgs &F, unsigned long long *smem) {
+__device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned int *s_new) {
     ScanCounters *c = F.c;
     const ScanArgs *A = F.A;
     const GridDesc *g = F.g;
@@ -1241,44 +1298,46 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem) {
             }
         }
         if (F.init_records) {
-            // default records of this warp's new blocks (multi-GPU: written into every replica by the block's owner)
+            // Default records of the tile's new blocks, 16 bytes per thread and step, by the whole CTA.  Multi-GPU: the
+            // block's owner writes the record into EVERY replica -- a peer may be ahead of us, and its results must not be
+            // overwritten by a default record that we write later; stores of one GPU to one peer arrive in order, so the
+            // owner's defaults land before the owner's results.
             const PeerTable *PT = A->peers;
             const int world = (PT && !PT->deferred) ? PT->world : 1, my_rank = PT ? PT->rank : 0;
             const bool mine = !PT || block_owner(key, t, PT->world, true) == PT->rank;
             if (PT && PT->deferred && mine && pl.is_new) F.dirty[pl.slot] = 1;
-            unsigned int todo = __ballot_sync(0xffffffffu, pl.is_new != 0u && mine);
-            const int lane = threadIdx.x & 31;
+            __syncthreads();
+            if (pl.is_new) s_new[rank] = mine ? pl.slot : kPad;
+            __syncthreads();
             const int nodes = P->nodes, st_off = P->st_off, words = P->rec_bytes >> 4;
             const float da = P->def_a, db = P->def_b;
             const unsigned int leaves = (unsigned int) (P->finest & 0xFF);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const unsigned int sl = __shfl_sync(0xffffffffu, pl.slot, src);
+            for (unsigned int idx = threadIdx.x; idx < tot * (unsigned int) words; idx += kFT) {
+                const unsigned int sl = s_new[idx / (unsigned int) words];
+                if (sl == kPad) continue;
+                const int w = (int) (idx % (unsigned int) words);
                 const size_t rec_off = (size_t) sl * (size_t) P->rec_bytes;
-                for (int w = lane; w < words; w += 32) {
-                    uint4 v;
-                    unsigned int *vw = reinterpret_cast<unsigned int *>(&v);
+                uint4 v;
+                unsigned int *vw = reinterpret_cast<unsigned int *>(&v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int byte0 = 16 * w + 4 * q;
-                        unsigned int word;
-                        if (byte0 + 4 <= st_off) word = __float_as_uint(((byte0 >> 2) & 1) ? db : da);
-                        else {
-                            word = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const int byte0 = 16 * w + 4 * q;
+                    unsigned int word;
+                    if (byte0 + 4 <= st_off) word = __float_as_uint(((byte0 >> 2) & 1) ? db : da);
+                    else {
+                        word = 0;
 #pragma unroll
-                            for (int bb = 0; bb < 4; ++bb) {
-                                const int nn = byte0 + bb - st_off;
-                                const unsigned int by = nn < nodes ? (unsigned int) LA3DM_UNKNOWN : (nn == nodes ? leaves : 0u);
-                                word |= by << (8 * bb);
-                            }
+                        for (int bb = 0; bb < 4; ++bb) {
+                            const int nn = byte0 + bb - st_off;
+                            const unsigned int by = nn < nodes ? (unsigned int) LA3DM_UNKNOWN : (nn == nodes ? leaves : 0u);
+                            word |= by << (8 * bb);
                         }
-                        vw[q] = word;
                     }
-                    reinterpret_cast<uint4 *>(F.pool + rec_off)[w] = v;
-                    for (int p = 0; p < world; ++p)
-                        if (p != my_rank) reinterpret_cast<uint4 *>(PT->pool[p] + rec_off)[w] = v;
+                    vw[q] = word;
                 }
+                reinterpret_cast<uint4 *>(F.pool + rec_off)[w] = v;
+                for (int p = 0; p < world; ++p)
+                    if (p != my_rank) reinterpret_cast<uint4 *>(PT->pool[p] + rec_off)[w] = v;
             }
         }
         if (!valid) continue;
@@ -1341,7 +1400,6 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
     vg_order<0>(F);                         grid_sync(bar, epoch, tr);
     vg_centroid<0>(F, smem, scratch);       grid_sync(bar, epoch, tr);
     beam_fill(F, smem, scratch);            grid_sync(bar, epoch, tr);
-    vg_keys<1>(F);                          grid_sync(bar, epoch, tr);
     vg_bits_count<1>(F, smem);              grid_sync(bar, epoch, tr);
     vg_bits_prefix<1>(F, smem);             grid_sync(bar, epoch, tr);
     vg_rank<1>(F);                          grid_sync(bar, epoch, tr);
@@ -1381,7 +1439,7 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_binning(const FusedArgs F) {
 // test blocks, their slots in the map, their neighbour plans
 __global__ void __launch_bounds__(kFT, 1) k_fused_plan(const FusedArgs F) {
     __shared__ unsigned long long smem[66];
-    __shared__ __align__(16) unsigned char scratch[1024];
+    __shared__ __align__(16) unsigned char scratch[4096];
     unsigned int epoch = 0;
     unsigned int *bar = F.bar + 2;
     unsigned long long *tr = F.trace ? F.trace + 128 : nullptr;
@@ -1390,7 +1448,7 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_plan(const FusedArgs F) {
     test_count(F, smem);                    grid_sync(bar, epoch, tr);
     test_place(F, smem, scratch);           grid_sync(bar, epoch, tr);
     plan_find(F);                           grid_sync(bar, epoch, tr);
-    plan_fill(F, smem);
+    plan_fill(F, smem, reinterpret_cast<unsigned int *>(scratch));
     __syncthreads();
     trace_mark(tr, 1);
 }
@@ -1475,7 +1533,12 @@ void Map::enqueue_fused(int stage) {
     void *args[] = {&F};
     const void *fn = stage == 0 ? (const void *) k_fused_frontend
                                 : (stage == 1 ? (const void *) k_fused_binning : (const void *) k_fused_plan);
-    LA3DM_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned int) num_sms), dim3(kFT), args, 0, stream));
+    // small scans: fewer CTAs, cheaper barriers (one CTA: the barrier is a __syncthreads)
+    static const size_t per_cta = getenv("LA3DM_FUSED_ITEMS_PER_CTA") ? (size_t) atoll(getenv("LA3DM_FUSED_ITEMS_PER_CTA")) : 1024;
+    const size_t items = stage == 0 ? std::max<size_t>(caps.points, caps.raw)
+                                    : (stage == 1 ? std::max<size_t>(caps.train, caps.cells / 4) : std::max<size_t>(caps.tests, caps.cells / 32));
+    const unsigned int grid = (unsigned int) std::min<size_t>((size_t) num_sms, std::max<size_t>(1, (items + per_cta - 1) / per_cta));
+    LA3DM_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kFT), args, 0, stream));
     ++launches;
 }
 
