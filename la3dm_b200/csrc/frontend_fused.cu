@@ -114,10 +114,10 @@ __device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch
     if (threadIdx.x == 0) {
         epoch += gridDim.x;
         const unsigned long long t0 = trace ? global_ns() : 0ull;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        // release: everything this CTA wrote (ordered before by the bar.sync above) is visible to whoever acquires the
+        // counter; acquire: ... and what the other CTAs wrote is visible to this CTA after the bar.sync below
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         while (ld_acquire(bar) < epoch) {}
-        __threadfence();
         if (trace && blockIdx.x == 0) {
             const unsigned int ph = epoch / gridDim.x;             // 1-based phase just finished
             trace[2 * ph] = t0;                                    // CTA 0 arrived
@@ -483,47 +483,63 @@ __device__ void vg_drop(const FusedArgs &F) {
     }
 }
 
-// Spans longer than kShortRun: list A a warp per span, list B a CTA per span (a warp per 32 of its indices).  Lane e holds
-// an index of the span and counts the smaller ones among all of them (32 at a time through shuffles); emit(position, index,
-// span) for every index.  The lists hand consecutive (= neighbouring, = similarly long) spans to different warps.
+// Spans longer than kShortRun.  List A (up to kWideRun indices): a warp per span, the span in registers (four indices per
+// lane), every index counts the smaller ones through shuffles.  List B (up to kFastRun): a CTA per span, the span in shared
+// memory, a thread per index.  emit(position, index, span) for every index.  The lists hand consecutive (= neighbouring,
+// = similarly long) spans to different warps / CTAs.
 template <typename Emit>
-__device__ __forceinline__ void order_chunk(const unsigned int *list, unsigned int f, unsigned int l, unsigned int c0, int lane,
-                                            unsigned int r, Emit &emit) {
-    const unsigned int x = c0 + lane < l ? list[f + c0 + lane] : kPad;
-    unsigned int rank = 0;
-    for (unsigned int c1 = 0; c1 < l; c1 += 32) {
-        const unsigned int y = c1 + lane < l ? list[f + c1 + lane] : kPad;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) rank += __shfl_sync(0xffffffffu, y, k) < x ? 1u : 0u;
-    }
-    if (c0 + lane < l) emit(f + rank, x, r);
-}
-
-template <typename Emit>
-__device__ inline void order_long_spans(const FusedArgs &F, int pass, const unsigned int *start, const unsigned int *list, Emit emit) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ inline void order_long_spans(const FusedArgs &F, int pass, const unsigned int *start, const unsigned int *list,
+                                        unsigned int *s_list /* [kFastRun + 4] */, Emit emit) {
+    const int lane = threadIdx.x & 31;
     const unsigned int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     const unsigned int nA = min(F.c->fz_nlong[pass][0], F.long_capA), nB = min(F.c->fz_nlong[pass][1], F.long_capB);
     for (unsigned int q = blockIdx.x; q < nB; q += gridDim.x) {
         const unsigned int r = F.longs[F.long_capA + q];
-        const unsigned int f = start[r], l = start[r + 1] - f;
-        for (unsigned int c0 = warp * 32u; c0 < l; c0 += kFT) order_chunk(list, f, l, c0, lane, r, emit);
+        const unsigned int f = start[r], l = min(start[r + 1] - f, kFastRun);
+        __syncthreads();
+        for (unsigned int j = threadIdx.x; j < ((l + 3u) & ~3u); j += kFT) s_list[j] = j < l ? list[f + j] : kPad;
+        __syncthreads();
+        for (unsigned int j0 = threadIdx.x; j0 < l; j0 += kFT) {
+            const unsigned int x = s_list[j0];
+            unsigned int rank = 0;
+            for (unsigned int j = 0; j < l; j += 4) {
+                const uint4 y = *reinterpret_cast<const uint4 *>(s_list + j);
+                rank += (y.x < x ? 1u : 0u) + (y.y < x ? 1u : 0u) + (y.z < x ? 1u : 0u) + (y.w < x ? 1u : 0u);
+            }
+            emit(f + rank, x, r);
+        }
     }
+    constexpr int kPer = kWideRun / 32;
     for (unsigned int q = gw; q < nA; q += nw) {
         const unsigned int r = F.longs[q];
-        const unsigned int f = start[r], l = start[r + 1] - f;
-        for (unsigned int c0 = 0; c0 < l; c0 += 32) order_chunk(list, f, l, c0, lane, r, emit);
+        const unsigned int f = start[r], l = min(start[r + 1] - f, kWideRun);
+        unsigned int v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) v[k] = lane + 32u * k < l ? list[f + lane + 32u * k] : kPad;
+#pragma unroll
+        for (int kx = 0; kx < kPer; ++kx) {
+            if (32u * kx >= l) break;
+            const unsigned int x = v[kx];
+            unsigned int rank = 0;
+#pragma unroll
+            for (int ky = 0; ky < kPer; ++ky) {
+                if (32u * ky >= l) break;
+#pragma unroll
+                for (int sft = 0; sft < 32; ++sft) rank += __shfl_sync(0xffffffffu, v[ky], sft) < x ? 1u : 0u;
+            }
+            if (lane + 32u * kx < l) emit(f + rank, x, r);
+        }
     }
 }
 
 // P8: ... and into input order: the place of an index = how many indices of the span are smaller
 template <int W>
-__device__ void vg_order(const FusedArgs &F) {
+__device__ void vg_order(const FusedArgs &F, unsigned char *scratch) {
     VGPass<W> V(F, false);
     if (V.pass || V.dead) return;
     const unsigned int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
     unsigned int *vsorted = F.vsorted;
-    order_long_spans(F, W, F.vstart, F.vlist, [vsorted](unsigned int pos, unsigned int idx, unsigned int) { vsorted[pos] = idx; });
+    order_long_spans(F, W, F.vstart, F.vlist, reinterpret_cast<unsigned int *>(scratch), [vsorted](unsigned int pos, unsigned int idx, unsigned int) { vsorted[pos] = idx; });
     for (unsigned int i0 = gt; i0 < V.n; i0 += 4 * gn) {
         unsigned int r[4], first[4], last[4];
 #pragma unroll
@@ -634,12 +650,37 @@ __device__ void vg_centroid(const FusedArgs &F, unsigned long long *smem, unsign
     }
     if (W == 1 && blockIdx.x == 0 && threadIdx.x == 0 && !V.dead) F.c->n_train = n_hits + nv;
     Box box;
-    // ---- long voxels first (they are the long poles): a warp each, points staged through shared memory
+    // ---- long voxels first (they are the long poles).  List B: a CTA each, all points gathered into shared memory at
+    // once, three threads add them up; list A: a warp each, staged kMidStage points at a time.
     if (!V.pass) {
         const unsigned int gw = gt >> 5, nw = gn >> 5;
         const unsigned int nA = min(F.c->fz_nlong[W][0], F.long_capA), nB = min(F.c->fz_nlong[W][1], F.long_capB);
-        for (unsigned int q = gw; q < nA + nB; q += nw) {
-            const unsigned int r2 = q < nB ? F.longs[F.long_capA + q] : F.longs[q - nB];
+        float(*cstage)[kFastRun] = reinterpret_cast<float(*)[kFastRun]>(scratch);     // [3][2048]
+        for (unsigned int q = blockIdx.x; q < nB; q += gridDim.x) {
+            const unsigned int r2 = F.longs[F.long_capA + q];
+            if (W == 1 && r2 == r0) continue;
+            const unsigned int run_first = F.vstart[r2], l = min(F.vstart[r2 + 1] - run_first, kFastRun);
+            __syncthreads();
+            for (unsigned int j = threadIdx.x; j < l; j += kFT) {
+                const float *p = V.in + (size_t) F.vsorted[run_first + j] * V.stride;
+                cstage[0][j] = p[0]; cstage[1][j] = p[1]; cstage[2][j] = p[2];
+            }
+            __syncthreads();
+            if (warp == 0) {
+                float acc = 0.f;
+                if (lane < 3) acc = seq_sum(0.f, cstage[lane], l) / (float) l;
+                const float cx = __shfl_sync(0xffffffffu, acc, 0), cy = __shfl_sync(0xffffffffu, acc, 1),
+                            cz = __shfl_sync(0xffffffffu, acc, 2);
+                if (lane == 0) {
+                    const float4 v = make_float4(cx, cy, cz, label);
+                    out[off + r2] = v;
+                    centroid_done<W>(F, r2, v, box);
+                }
+            }
+        }
+        __syncthreads();
+        for (unsigned int q = gw; q < nA; q += nw) {
+            const unsigned int r2 = F.longs[q];
             if (W == 1 && r2 == r0) continue;
             const unsigned int run_first = F.vstart[r2], run_last = F.vstart[r2 + 1];
             float acc = 0.f;
@@ -824,7 +865,7 @@ __device__ void beam_fill(const FusedArgs &F, unsigned long long *smem, unsigned
             out[q] = make_float4(sx, sy, sz, __int_as_float(w));
             if (keys2) {
                 unsigned int cell = kPad;                                  // (an origin copy stays out of the lists)
-                if (e1) { cell = vg_cell(f2, inv, sx, sy, sz); set_bit(F.bits, cell); }
+                if (e1) { cell = vg_cell(f2, inv, sx, sy, sz); atomicOr(&F.bits[cell >> 5], 1u << (cell & 31)); }
                 kout[q] = cell;
             }
         }
@@ -938,14 +979,14 @@ __device__ void bin_members(const FusedArgs &F) {
     const unsigned int n1 = (unsigned int) g->n[1], n2 = (unsigned int) g->n[2];
     const unsigned int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
     bool ovf = false;
-    for (unsigned int i0 = gt; i0 < n; i0 += 2 * gn) {
-        float4 p[2];
-        unsigned int mx[2], my[2], mz[2], cell0[2], tk[2];
-        int rx[2], ry[2], rz[2];
+    for (unsigned int i0 = gt; i0 < n; i0 += 4 * gn) {
+        float4 p[4];
+        unsigned int mx[4], my[4], mz[4], cell0[4], tk[4];
+        int rx[4], ry[4], rz[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) { const unsigned int i = i0 + k * gn; if (i < n) p[k] = F.xy[i]; }
+        for (int k = 0; k < 4; ++k) { const unsigned int i = i0 + k * gn; if (i < n) p[k] = F.xy[i]; }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const unsigned int i = i0 + k * gn;
             mx[k] = my[k] = mz[k] = 0;
             if (i >= n) continue;
@@ -955,7 +996,7 @@ __device__ void bin_members(const FusedArgs &F) {
         }
         // the common case first: one block per entry, both tickets in flight together
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 4; ++k) {
             cell0[k] = kPad;
             if (!(mx[k] && my[k] && mz[k])) continue;
             const int a = __ffs(mx[k]) - 1, b = __ffs(my[k]) - 1, d = __ffs(mz[k]) - 1;
@@ -963,7 +1004,7 @@ __device__ void bin_members(const FusedArgs &F) {
             tk[k] = atomicAdd(&F.cell_cnt[cell0[k]], 1u);
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const unsigned int i = i0 + k * gn;
             if (i >= n) continue;
             F.mcell[i] = cell0[k];
@@ -1126,7 +1167,7 @@ __device__ __forceinline__ void bin_order_one(const FusedArgs &F, const BinEmit 
     emit(first + rank, i, cell);
 }
 
-__device__ void bin_order(const FusedArgs &F) {
+__device__ void bin_order(const FusedArgs &F, unsigned char *scratch) {
     ScanCounters *c = F.c;
     const bool dead = ld_volatile(&c->overflow) != 0u;
     const unsigned int n = dead ? 0u : min(c->n_train, F.train_cap);
@@ -1136,7 +1177,7 @@ __device__ void bin_order(const FusedArgs &F) {
     const unsigned int n_db = dead ? 0u : min(c->n_data_blocks, F.members_cap);
     const unsigned int *db_id = F.db_id, *db_start = F.db_start;
     // long spans: a warp / a CTA each (the cell of a span's entries = its data block's cell)
-    if (!dead) order_long_spans(F, 2, db_start, F.mlist, [&emit, db_id](unsigned int pos, unsigned int i, unsigned int d) { emit(pos, i, db_id[d]); });
+    if (!dead) order_long_spans(F, 2, db_start, F.mlist, reinterpret_cast<unsigned int *>(scratch), [&emit, db_id](unsigned int pos, unsigned int i, unsigned int d) { emit(pos, i, db_id[d]); });
     (void) n_db;
     for (unsigned int i0 = gt; i0 < n; i0 += 2 * gn) {
         unsigned int cell[2];
@@ -1397,7 +1438,7 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
     vg_span_count<0>(F, smem);              grid_sync(bar, epoch, tr);
     vg_span_place<0>(F, smem);              grid_sync(bar, epoch, tr);
     vg_drop<0>(F);                          grid_sync(bar, epoch, tr);
-    vg_order<0>(F);                         grid_sync(bar, epoch, tr);
+    vg_order<0>(F, scratch);                         grid_sync(bar, epoch, tr);
     vg_centroid<0>(F, smem, scratch);       grid_sync(bar, epoch, tr);
     beam_fill(F, smem, scratch);            grid_sync(bar, epoch, tr);
     vg_bits_count<1>(F, smem);              grid_sync(bar, epoch, tr);
@@ -1406,7 +1447,7 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
     vg_span_count<1>(F, smem);              grid_sync(bar, epoch, tr);
     vg_span_place<1>(F, smem);              grid_sync(bar, epoch, tr);
     vg_drop<1>(F);                          grid_sync(bar, epoch, tr);
-    vg_order<1>(F);                         grid_sync(bar, epoch, tr);
+    vg_order<1>(F, scratch);                         grid_sync(bar, epoch, tr);
     vg_centroid<1>(F, smem, scratch);
     __syncthreads();
     trace_mark(tr, 1);
@@ -1431,7 +1472,7 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_binning(const FusedArgs F) {
     bin_cell_count(F, smem);                grid_sync(bar, epoch, tr);
     bin_cell_place(F, smem);                grid_sync(bar, epoch, tr);
     bin_drop(F);                            grid_sync(bar, epoch, tr);
-    bin_order(F);
+    bin_order(F, scratch);
     __syncthreads();
     trace_mark(tr, 1);
 }
