@@ -197,6 +197,16 @@ int la3dm_export_blocks(la3dm_map *map, int64_t *keys, la3dm_node *nodes, size_t
 int64_t la3dm_num_leaves(la3dm_map *map);
 int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t *n_out);
 
+/* Incremental mirror for the server loop.  The reference's server re-walks the WHOLE map after every scan to rebuild
+ * its marker arrays and skips everything that is not OCCUPIED / FREE (src/bgkoctomap/bgkoctomap_server.cpp:94-144).
+ * This returns, compacted on the GPU, only the leaves whose state is in state_mask (bit s = state s, e.g.
+ * (1 << LA3DM_OCCUPIED) | (1 << LA3DM_FREE); 0xFF = all) of the blocks that were test blocks of a scan (or were
+ * imported / loaded) since the last call with clear != 0, sorted like la3dm_export_leaves, and the sorted keys of those
+ * blocks: the mirror REPLACES what it holds for every listed block (a block whose wanted leaves have all gone is listed
+ * with no leaves).  leaves == NULL: counts only (nothing is cleared); block_keys may be NULL. */
+int la3dm_export_touched(la3dm_map *map, unsigned int state_mask, la3dm_leaf *leaves, size_t capacity_leaves,
+                         size_t *n_leaves, int64_t *block_keys, size_t capacity_blocks, size_t *n_blocks, int clear);
+
 /* Point query, batched: replaces  OcTreeNode search(point3f p) / search(float x, float y, float z)
  * (include/bgkoctomap/bgkoctomap.h:315-319; src/bgkoctomap/bgkoctomap.cpp:554-574 -> Block::search,
  * src/bgkoctomap/bgkblock.cpp:132-156).  xyz: HOST pointer, n points, stride_bytes per record; out: n HOST records.

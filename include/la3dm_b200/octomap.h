@@ -189,6 +189,19 @@ public:
     LeafIterator end_leaf() const { refresh(); return LeafIterator(this, leaves_.size()); }
     size_t num_leaves() const { refresh(); return leaves_.size(); }
 
+    /// The server loop without the full-map walk (src/bgkoctomap/bgkoctomap_server.cpp:94-144 visits every leaf of the
+    /// map after every scan and keeps the OCCUPIED / FREE ones): the leaves in the wanted states of the blocks the scans
+    /// since the previous call touched, plus the keys of those blocks -- replace what the marker arrays hold for the
+    /// listed blocks (la3dm_export_touched).  state_mask: bit s = state s.
+    void touched_leaves(unsigned int state_mask, std::vector<la3dm_leaf> &leaves, std::vector<int64_t> &block_keys) const {
+        size_t nl = 0, nb = 0;
+        check(la3dm_export_touched(h_, state_mask, nullptr, 0, &nl, nullptr, 0, &nb, 0));
+        leaves.resize(nl ? nl : 1);
+        block_keys.resize(nb);
+        if (nb) check(la3dm_export_touched(h_, state_mask, leaves.data(), leaves.size(), &nl, block_keys.data(), nb, &nb, 1));
+        leaves.resize(nl);
+    }
+
     /// search(x, y, z) (include/bgkoctomap/bgkoctomap.h:315-319): the leaf that holds the point, looked up on the
     /// device (la3dm_search); an UNKNOWN default node if the block does not exist, like upstream's `OcTreeNode()`.
     /// The reference's Block::search is only right for block_depth 4; this one is right for any depth.

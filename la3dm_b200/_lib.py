@@ -66,6 +66,8 @@ SYMBOLS = {
     "la3dm_export_blocks": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "la3dm_num_leaves": (C.c_int64, [_P]),
     "la3dm_export_leaves": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "la3dm_export_touched": (C.c_int, [_P, C.c_uint, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_size_t,
+                                       C.POINTER(C.c_size_t), C.c_int]),
     "la3dm_search": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, _P]),
     "la3dm_raycast": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, _P, _P]),
     "la3dm_import_blocks": (C.c_int, [_P, _P, _P, C.c_size_t]),

@@ -224,6 +224,14 @@ int la3dm_export_leaves(la3dm_map *map, la3dm_leaf *out, size_t capacity, size_t
     return guarded(map, [&] { map->m.export_leaves(out, capacity, n_out); });
 }
 
+int la3dm_export_touched(la3dm_map *map, unsigned int state_mask, la3dm_leaf *leaves, size_t capacity_leaves,
+                         size_t *n_leaves, int64_t *block_keys, size_t capacity_blocks, size_t *n_blocks, int clear) {
+    if (!map) return LA3DM_ERR_INVALID;
+    return guarded(map, [&] {
+        map->m.export_touched(state_mask, leaves, capacity_leaves, n_leaves, block_keys, capacity_blocks, n_blocks, clear != 0);
+    });
+}
+
 int la3dm_search(la3dm_map *map, const float *xyz, size_t n, size_t stride_bytes, int finest_only, la3dm_leaf *out) {
     if (!map) return LA3DM_ERR_INVALID;
     return guarded(map, [&] { map->m.search(xyz, n, stride_bytes, false, finest_only, out); });

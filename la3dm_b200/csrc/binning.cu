@@ -370,7 +370,7 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
        const GridDesc *__restrict__ g, const unsigned int *__restrict__ cell_db,
        const unsigned int *__restrict__ db_start, long long *hkeys, int *hvals, size_t mask, long long *keys,
        NeighbourPlan *plan, unsigned int *plan_db, unsigned int *heavy_list, unsigned int *light_list,
-       uint4 *mega_list, unsigned int *chunk_mega, unsigned char *dirty, unsigned int *cell_test,
+       uint4 *mega_list, unsigned int *chunk_mega, unsigned char *dirty, unsigned char *touched, unsigned int *cell_test,
        const unsigned int *__restrict__ tile_sums,
        unsigned int n_tiles, int prescanned, unsigned char *pool, const DevParams *__restrict__ P, int init_records) {
     __shared__ unsigned int smem[66];
@@ -439,6 +439,7 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
         }
     }
     if (!valid) return;
+    touched[pl.slot] = 1;                      // read side: la3dm_export_touched
     if (cell_test) cell_test[test_id[t]] = t + 1;
     const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
     unsigned int tot = 0;
@@ -506,6 +507,11 @@ void Map::ensure_pool(size_t blocks, bool exact) {
             const size_t old = dirty.cap;
             dirty.grow_keep(want, stream);
             if (dirty.cap > old) LA3DM_CUDA(cudaMemsetAsync(dirty.as<unsigned char>() + old, 0, dirty.cap - old, stream));
+        }
+        {
+            const size_t old = touched.cap;
+            touched.grow_keep(want, stream);
+            if (touched.cap > old) LA3DM_CUDA(cudaMemsetAsync(touched.as<unsigned char>() + old, 0, touched.cap - old, stream));
         }
         pool_cap = want;
         invalidate_graph();
@@ -598,7 +604,7 @@ void Map::enqueue_binning() {
         hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(), plan.as<NeighbourPlan>(),
         hp.method == LA3DM_GP ? plan_db.as<unsigned int>() : nullptr,
         hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr, light_list.as<unsigned int>(),
-        mega_list.as<uint4>(), chunk_mega.as<unsigned int>(), dirty.as<unsigned char>(),
+        mega_list.as<uint4>(), chunk_mega.as<unsigned int>(), dirty.as<unsigned char>(), touched.as<unsigned char>(),
         hp.method == LA3DM_GP ? cell_test.as<unsigned int>() : nullptr, tile_sums, (unsigned int) p_tiles,
         p_prescanned, pool.as<unsigned char>(), d_params, hp.method == LA3DM_BGK ? 1 : 0);
     ++launches;

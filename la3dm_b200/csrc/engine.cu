@@ -40,8 +40,14 @@ __global__ void k_gather_keys(const long long *__restrict__ keys, const unsigned
     if (i < n) out[i] = keys[order[i]];
 }
 
+// state_mask: bit s set = leaves in state s are wanted (0xFF: all)
+__device__ __forceinline__ bool leaf_wanted(const unsigned char *bst, const DevParams &P, int d, int i, unsigned int state_mask) {
+    return node_is_leaf(bst, P, d, i) && ((state_mask >> (bst[P.layer_off[d] + i] & 7)) & 1u);
+}
+
 __global__ void k_leaf_count(const unsigned char *__restrict__ pool, const unsigned int *__restrict__ order,
-                             unsigned int n_blocks, const DevParams *__restrict__ Pg, unsigned int *cnt) {
+                             unsigned int n_blocks, const DevParams *__restrict__ Pg, unsigned int state_mask,
+                             unsigned int *cnt) {
     // one warp per block
     const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_blocks) return;
@@ -50,7 +56,7 @@ __global__ void k_leaf_count(const unsigned char *__restrict__ pool, const unsig
     unsigned int c = 0;
     for (int d = 0; d < P.depth; ++d) {
         const int n = 1 << (3 * d);
-        for (int i = lane; i < n; i += 32) c += node_is_leaf(bst, P, d, i) ? 1u : 0u;
+        for (int i = lane; i < n; i += 32) c += leaf_wanted(bst, P, d, i, state_mask) ? 1u : 0u;
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) cnt[w] = c;
@@ -60,7 +66,7 @@ __global__ void k_leaf_count(const unsigned char *__restrict__ pool, const unsig
 __global__ void k_leaf_fill(const unsigned char *__restrict__ pool, const long long *__restrict__ keys,
                             const unsigned int *__restrict__ order, unsigned int n_blocks,
                             const DevParams *__restrict__ Pg, const float3 *__restrict__ lut,
-                            const unsigned int *__restrict__ off, la3dm_leaf *out) {
+                            const unsigned int *__restrict__ off, unsigned int state_mask, la3dm_leaf *out) {
     const unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_blocks) return;
     const DevParams &P = *Pg;
@@ -76,7 +82,7 @@ __global__ void k_leaf_fill(const unsigned char *__restrict__ pool, const long l
         const int n = 1 << (3 * d);
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
-            const bool leaf = i < n && node_is_leaf(bst, P, d, i);
+            const bool leaf = i < n && leaf_wanted(bst, P, d, i, state_mask);
             const unsigned int m = __ballot_sync(0xffffffffu, leaf);
             if (leaf) {
                 const unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
@@ -94,6 +100,22 @@ __global__ void k_leaf_fill(const unsigned char *__restrict__ pool, const long l
 __global__ void k_leaf_total(const unsigned int *__restrict__ cnt, const unsigned int *__restrict__ off,
                              unsigned int n, ScanCounters *c) {
     c->n_leaves = n ? cnt[n - 1] + off[n - 1] : 0;
+}
+
+// slots of the blocks touched since the last clearing export, with their keys (unordered)
+__global__ void k_touched_collect(const unsigned char *__restrict__ touched, const long long *__restrict__ keys,
+                                  unsigned int n_blocks, long long *out_keys, unsigned int *out_slots, unsigned int *count) {
+    const unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool t = slot < n_blocks && touched[slot] != 0;
+    const unsigned int m = __ballot_sync(0xffffffffu, t);
+    unsigned int base = 0;
+    if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(count, (unsigned int) __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (t) {
+        const unsigned int pos = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+        out_keys[pos] = keys[slot];
+        out_slots[pos] = slot;
+    }
 }
 
 unsigned int grow_to(unsigned int need, unsigned int floor_) {
@@ -546,7 +568,7 @@ long long Map::count_leaves() {
     leaf_cnt.reserve(n * 4, stream);
     leaf_off.reserve(n * 4, stream);
     k_leaf_count<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
-        pool.as<unsigned char>(), order, (unsigned int) n, d_params, leaf_cnt.as<unsigned int>());
+        pool.as<unsigned char>(), order, (unsigned int) n, d_params, 0xFFu, leaf_cnt.as<unsigned int>());
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (int) n, stream);
     export_tmp.reserve(tmp, stream);
@@ -568,8 +590,79 @@ void Map::export_leaves(la3dm_leaf *out, size_t cap, size_t *n_out) {
     leaf_out.reserve((size_t) total * sizeof(la3dm_leaf), stream);
     k_leaf_fill<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
         pool.as<unsigned char>(), keys.as<long long>(), block_order.as<unsigned int>(), (unsigned int) n, d_params,
-        d_lut, leaf_off.as<unsigned int>(), leaf_out.as<la3dm_leaf>());
+        d_lut, leaf_off.as<unsigned int>(), 0xFFu, leaf_out.as<la3dm_leaf>());
     LA3DM_CUDA(cudaMemcpyAsync(out, leaf_out.p, (size_t) total * sizeof(la3dm_leaf), cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace la3dm_b200
+
+namespace la3dm_b200 {
+
+// leaves (filtered by state) of the blocks order[0 .. n), in that order; out == nullptr: count only
+void Map::leaves_of(const unsigned int *order, size_t n, unsigned int state_mask, la3dm_leaf *out, size_t cap, size_t *n_out) {
+    leaf_cnt.reserve(n * 4, stream);
+    leaf_off.reserve(n * 4, stream);
+    k_leaf_count<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
+        pool.as<unsigned char>(), order, (unsigned int) n, d_params, state_mask, leaf_cnt.as<unsigned int>());
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (int) n, stream);
+    export_tmp.reserve(tmp, stream);
+    LA3DM_CUDA(cub::DeviceScan::ExclusiveSum(export_tmp.p, tmp, leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(),
+                                             (int) n, stream));
+    k_leaf_total<<<1, 1, 0, stream>>>(leaf_cnt.as<unsigned int>(), leaf_off.as<unsigned int>(), (unsigned int) n, d_cnt);
+    unsigned int total = 0;
+    LA3DM_CUDA(cudaMemcpyAsync(&total, &d_cnt->n_leaves, 4, cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    if (n_out) *n_out = total;
+    if (!out || total == 0) return;
+    if (cap < (size_t) total) throw StatusError{LA3DM_ERR_INVALID, "leaf export: capacity too small"};
+    leaf_out.reserve((size_t) total * sizeof(la3dm_leaf), stream);
+    k_leaf_fill<<<ceil_div((long long) n * 32, kThreads), kThreads, 0, stream>>>(
+        pool.as<unsigned char>(), keys.as<long long>(), order, (unsigned int) n, d_params, d_lut,
+        leaf_off.as<unsigned int>(), state_mask, leaf_out.as<la3dm_leaf>());
+    LA3DM_CUDA(cudaMemcpyAsync(out, leaf_out.p, (size_t) total * sizeof(la3dm_leaf), cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+}
+
+// The server loop's mirror (bgkoctomap_server.cpp:94-144 walks the WHOLE map after every scan to rebuild its marker
+// arrays): only the blocks that were test blocks of a scan since the last clearing call, only the leaves whose state is in
+// state_mask.  block_keys lists every such block (sorted) -- a mirror replaces all it holds for those blocks, so a block
+// whose wanted leaves have all gone (pruned, reclassified) is cleared too.
+void Map::export_touched(unsigned int state_mask, la3dm_leaf *out, size_t cap, size_t *n_out, int64_t *block_keys,
+                         size_t cap_blocks, size_t *n_blocks_out, bool clear) {
+    check_synced();
+    LA3DM_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t) n_blocks;
+    if (n_out) *n_out = 0;
+    if (n_blocks_out) *n_blocks_out = 0;
+    if (n == 0) return;
+    for (int i = 0; i < 2; ++i) { order_keys[i].reserve(n * 8, stream); order_vals[i].reserve(n * 4, stream); }
+    unsigned int *d_count = &d_cnt->n_leaves;                                  // (scratch counter between scans)
+    LA3DM_CUDA(cudaMemsetAsync(d_count, 0, 4, stream));
+    k_touched_collect<<<ceil_div((long long) n, kThreads), kThreads, 0, stream>>>(
+        touched.as<unsigned char>(), keys.as<long long>(), (unsigned int) n, order_keys[0].as<long long>(),
+        order_vals[0].as<unsigned int>(), d_count);
+    unsigned int nt = 0;
+    LA3DM_CUDA(cudaMemcpyAsync(&nt, d_count, 4, cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    if (n_blocks_out) *n_blocks_out = nt;
+    if (nt == 0) return;
+    // by key: the order of the full export
+    cub::DoubleBuffer<long long> dk(order_keys[0].as<long long>(), order_keys[1].as<long long>());
+    cub::DoubleBuffer<unsigned int> dv(order_vals[0].as<unsigned int>(), order_vals[1].as<unsigned int>());
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int) nt, 0, 60, stream);
+    export_tmp.reserve(tmp, stream);
+    LA3DM_CUDA(cub::DeviceRadixSort::SortPairs(export_tmp.p, tmp, dk, dv, (int) nt, 0, 60, stream));
+    block_order.reserve((size_t) nt * 4, stream);
+    LA3DM_CUDA(cudaMemcpyAsync(block_order.p, dv.Current(), (size_t) nt * 4, cudaMemcpyDeviceToDevice, stream));
+    if (block_keys) {
+        if (cap_blocks < nt) throw StatusError{LA3DM_ERR_INVALID, "export_touched: block capacity too small"};
+        LA3DM_CUDA(cudaMemcpyAsync(block_keys, dk.Current(), (size_t) nt * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    leaves_of(block_order.as<unsigned int>(), nt, state_mask, out, cap, n_out);
+    if (clear && out) LA3DM_CUDA(cudaMemsetAsync(touched.p, 0, n, stream));
     LA3DM_CUDA(cudaStreamSynchronize(stream));
 }
 

@@ -90,6 +90,7 @@ struct Map {
     DevBuf peer_flags;              // [kMaxPeers] u64, written by the peers
     bool peers_share_device = false;   // a peer replica lives on this very device (single-GPU tests)
     bool peers_attached = false, peers_deferred = false, peers_unsynced = false;
+    DevBuf touched;                 // [pool_cap] bytes: block was a test block of a scan since the last la3dm_export_touched(clear)
     DevBuf dirty;                   // [pool_cap] bytes: block changed since the last la3dm_peer_sync (deferred mode)
     unsigned long long sync_seq = 0;
     unsigned long long scan_seq = 0;
@@ -142,6 +143,9 @@ struct Map {
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();
     void export_leaves(la3dm_leaf *out, size_t cap, size_t *n);
+    void export_touched(unsigned int state_mask, la3dm_leaf *out, size_t cap, size_t *n, int64_t *block_keys,
+                        size_t cap_blocks, size_t *n_blocks_out, bool clear);
+    void leaves_of(const unsigned int *order, size_t n, unsigned int state_mask, la3dm_leaf *out, size_t cap, size_t *n_out);
     void sorted_block_order(DevBuf &order, size_t n);
     // query / import / serialisation (query.cu)
     void search(const float *xyz, size_t n, size_t stride_bytes, bool device_ptr, int finest_only, la3dm_leaf *out);

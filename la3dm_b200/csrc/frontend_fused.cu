@@ -78,7 +78,7 @@ struct FusedArgs {
     unsigned int *plan_db, *heavy_list, *light_list;
     uint4 *mega_list;
     unsigned int *chunk_mega;
-    unsigned char *dirty;
+    unsigned char *dirty, *touched;
     long long *hkeys;
     int *hvals;
     size_t hmask;
@@ -1382,6 +1382,7 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
             }
         }
         if (!valid) continue;
+        F.touched[pl.slot] = 1;                // read side: la3dm_export_touched
         if (F.cell_test) F.cell_test[tid_cell] = t + 1;
         if (F.heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank) {
             if (totp > kMegaTot) {
@@ -1565,7 +1566,7 @@ void Map::enqueue_fused(int stage) {
     F.heavy_list = hp.method == LA3DM_BGK ? heavy_list.as<unsigned int>() : nullptr;
     F.light_list = light_list.as<unsigned int>();
     F.mega_list = mega_list.as<uint4>(); F.chunk_mega = chunk_mega.as<unsigned int>();
-    F.dirty = dirty.as<unsigned char>();
+    F.dirty = dirty.as<unsigned char>(); F.touched = touched.as<unsigned char>();
     F.hkeys = hkeys.as<long long>(); F.hvals = hvals.as<int>(); F.hmask = hash_cap - 1;
     F.keys = keys.as<long long>(); F.pool = pool.as<unsigned char>();
     F.tests_cap = caps.tests;

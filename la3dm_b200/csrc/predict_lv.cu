@@ -230,7 +230,7 @@ __global__ void k_lv_active(const GridDesc *__restrict__ g, const QGrid *__restr
 
 // Every block of the bbox grid exists after the scan (:140-148).  First kernel that touches the persistent map.
 __global__ void k_lv_blocks(const GridDesc *__restrict__ g, ScanCounters *c, const ScanArgs *__restrict__ A,
-                            long long *hkeys, int *hvals, size_t mask, long long *keys, unsigned int *blk_slot,
+                            long long *hkeys, int *hvals, size_t mask, long long *keys, unsigned char *touched, unsigned int *blk_slot,
                             unsigned char *blk_flags, unsigned int active_cap) {
     if (c->overflow) return;
     if (c->lv_active > active_cap) {      // checked here, before anything is written
@@ -250,6 +250,7 @@ __global__ void k_lv_blocks(const GridDesc *__restrict__ g, ScanCounters *c, con
         blk_flags[bc] = 1;                // new: record to be initialised
     }
     blk_slot[bc] = (unsigned int) slot;
+    touched[slot] = 1;                         // read side: la3dm_export_touched
 }
 
 // default nodes for the new blocks: (prior_A, prior_B), UNKNOWN, !classified  (bgklvoctree_node.h:35)
@@ -511,7 +512,7 @@ void Map::enqueue_lv() {
                                                lv_active.as<uint2>(), caps.lv_active, caps.tests);
     k_lv_blocks<<<ceil_div(caps.tests, kThreads), kThreads, 0, stream>>>(
         d_grid, d_cnt, d_args, hkeys.as<long long>(), hvals.as<int>(), hash_cap - 1, keys.as<long long>(),
-        lv_blk_slot.as<unsigned int>(), lv_blk_flags.as<unsigned char>(), caps.lv_active);
+        touched.as<unsigned char>(), lv_blk_slot.as<unsigned int>(), lv_blk_flags.as<unsigned char>(), caps.lv_active);
     k_lv_init_new<<<wide, kThreads, 0, stream>>>(d_grid, d_cnt, d_params, lv_blk_slot.as<unsigned int>(),
                                                  lv_blk_flags.as<unsigned char>(), pool.as<unsigned char>(),
                                                  caps.lv_active);

@@ -263,6 +263,7 @@ void Map::import_blocks(const int64_t *in_keys, const la3dm_node *in_nodes, size
     LA3DM_CUDA(cudaMemcpyAsync(export_buf.p, in_nodes, total * sizeof(la3dm_node), cudaMemcpyHostToDevice, stream));
     k_unpack_nodes<<<ceil_div((long long) total, kThreads), kThreads, 0, stream>>>(
         export_buf.as<la3dm_node>(), (unsigned int) n, d_params, pool.as<unsigned char>());
+    LA3DM_CUDA(cudaMemsetAsync(touched.p, 1, n, stream));     // an imported block is news to an incremental mirror
     n_blocks = (long long) n;
     try {
         rebuild_hash();

@@ -146,6 +146,20 @@ class _OctoMapBase:
             self._check(self._lib.la3dm_export_leaves(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def touched_leaves(self, state_mask=0xFF, clear=True):
+        """(block_keys, leaves) of the blocks touched since the last clearing call: the server loop's incremental mirror
+        (la3dm_export_touched).  Replace everything held for the listed blocks by the returned leaves."""
+        nl, nb = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._lib.la3dm_export_touched(self._h, state_mask, None, 0, C.byref(nl), None, 0, C.byref(nb), 0))
+        keys = np.zeros(nb.value, np.int64)
+        out = np.zeros(nl.value, LEAF_DTYPE)
+        if nb.value:
+            # (with no wanted leaves at all the clearing still has to happen: a one-record dummy buffer keeps `leaves` non-NULL)
+            buf = out if nl.value else np.zeros(1, LEAF_DTYPE)
+            self._check(self._lib.la3dm_export_touched(self._h, state_mask, buf.ctypes.data, max(nl.value, 1), C.byref(nl),
+                                                       keys.ctypes.data, nb.value, C.byref(nb), 1 if clear else 0))
+        return keys, out
+
     def blocks(self):
         """(keys [B], nodes [B, nodes_per_block]) in the reference's Block/OcTree layout, sorted by key."""
         n = C.c_size_t(0)

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <utility>
+#include <map>
 #include <vector>
 
 #include "la3dm_b200/octomap.h"
@@ -23,6 +24,7 @@ int main(int argc, char **argv) {
     fclose(f);
     // config/methods/bgkoctomap.yaml
     la3dm::BGKOctoMap map(0.1f, 3, 1.0f, 0.2f, 0.3f, 0.7f, 100.0f, 0.001f, 0.001f);
+    std::map<int64_t, std::vector<la3dm_leaf>> mirror;
     for (int s = 0; s < n_scans; ++s) {
         Cloud cloud;
         cloud.points.resize(n_pts);
@@ -32,6 +34,12 @@ int main(int argc, char **argv) {
         }
         la3dm::vec3f origin(org[3 * s], org[3 * s + 1], org[3 * s + 2]);
         map.insert_pointcloud(cloud, origin, map.get_resolution(), 0.5f, 8.0f);   // static node: ds = resolution
+        // the server loop's marker arrays (bgkoctomap_server.cpp:94-144) kept from the blocks this scan touched
+        std::vector<la3dm_leaf> lv;
+        std::vector<int64_t> bk;
+        map.touched_leaves((1u << LA3DM_FREE) | (1u << LA3DM_OCCUPIED), lv, bk);
+        for (int64_t k : bk) mirror.erase(k);
+        for (const la3dm_leaf &l : lv) mirror[l.block_key].push_back(l);
     }
     long n = 0, nf = 0, no = 0, nu = 0;
     double sp = 0;
@@ -73,6 +81,12 @@ int main(int argc, char **argv) {
         la3dm::BGKOctoMap side(0.1f, 3, 1.0f, 0.2f, 0.3f, 0.7f, 100.0f, 0.001f, 0.001f);
         side.insert_training_data(xy);
         if (side.num_blocks() == 0 || side.search(org[0] + 0.5f, org[1], org[2]).get_prob() <= 0.9f) ++ray_bad;
+    }
+    {   // the incremental mirror must hold exactly the FREE / OCCUPIED leaves of the full walk above
+        long mf = 0, mo = 0;
+        for (const auto &kv : mirror)
+            for (const la3dm_leaf &l : kv.second) (l.state == LA3DM_FREE ? mf : mo) += 1;
+        if (mf != nf || mo != no) ++ray_bad;
     }
     la3dm::vec3f mn, mx;
     map.get_bbox(mn, mx);

@@ -234,3 +234,45 @@ def test_raycast_depth_3_is_consistent_with_search(scans):
         g = g[g["depth"] >= 0]
         s = m.search(np.stack([g["x"], g["y"], g["z"]], 1), finest_only=True)
         assert s.tobytes() == g.tobytes()
+
+
+def test_incremental_export_mirrors_the_map(scans):
+    """la3dm_export_touched: the server loop's mirror (bgkoctomap_server.cpp:94-144 keeps the OCCUPIED / FREE leaves of
+    the whole map) maintained from the blocks each scan touched; after every scan it must equal the filtered full
+    export.  Also: nothing to report without a scan in between, and a loaded map reports everything."""
+    import la3dm_b200
+    from test_gpu_bgk import new_map
+    pts, org = scans["sim_unstructured"]
+    m = new_map()
+    mask = (1 << 0) | (1 << 1)                       # LA3DM_FREE | LA3DM_OCCUPIED (include/la3dm_b200.h)
+    mirror = {}
+    for s in range(6):
+        m.insert_pointcloud(pts[s], org[s], RES, FREE_RES["bgk"], MAX_RANGE)
+        st = m.last_stats()
+        keys, lv = m.touched_leaves(mask)
+        assert len(keys) == st["n_test_blocks"], (len(keys), st["n_test_blocks"])
+        assert np.all(np.diff(keys) > 0)
+        assert np.isin(lv["block_key"], keys).all() and np.isin(lv["state"], (0, 1)).all()
+        for k in keys:
+            mirror.pop(int(k), None)
+        for k in np.unique(lv["block_key"]):
+            mirror[int(k)] = lv[lv["block_key"] == k]
+        full = m.leaves()
+        want = full[np.isin(full["state"], (0, 1))]
+        got = np.concatenate([mirror[k] for k in sorted(mirror)]) if mirror else want[:0]
+        assert got.tobytes() == want.tobytes(), s
+        k2, l2 = m.touched_leaves(mask)
+        assert len(k2) == 0 and len(l2) == 0
+    # unfiltered, not clearing: twice the same
+    m.insert_pointcloud(pts[6], org[6], RES, FREE_RES["bgk"], MAX_RANGE)
+    ka, la = m.touched_leaves(0xFF, clear=False)
+    kb, lb = m.touched_leaves(0xFF, clear=True)
+    assert np.array_equal(ka, kb) and la.tobytes() == lb.tobytes() and len(la) > 0
+    full = m.leaves()
+    assert la.tobytes() == full[np.isin(full["block_key"], ka)].tobytes()
+    # a map filled by import reports every block once
+    keys, nodes = m.blocks()
+    m2 = new_map()
+    m2.import_blocks(keys, nodes)
+    kc, lc = m2.touched_leaves(0xFF)
+    assert np.array_equal(kc, keys) and lc.tobytes() == full.tobytes()
