@@ -363,6 +363,7 @@ void Map::ensure_workspace() {
                                 hp.method == LA3DM_GP ? scan_temp_bytes(caps.members) : (size_t) 0);
     if (tmp > cub_tmp_bytes) { moved |= cub_tmp.reserve(tmp, stream); cub_tmp_bytes = tmp; }
     if (hp.method == LA3DM_BGK || hp.method == LA3DM_GP) moved |= ensure_fused_workspace();
+    if (hp.method == LA3DM_BGKL) moved |= ensure_bgkl_workspace();
     if (moved) invalidate_graph();
 }
 

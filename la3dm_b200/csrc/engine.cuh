@@ -53,6 +53,7 @@ struct Map {
     DevBuf test_id, plan, heavy_list, light_list, mega_list, chunk_mega, mega_acc;
     DevBuf gp_sizes, gp_off, gp_store, gp_scratch, gp_mv, plan_db;   // GPOctoMap: factor storage, per-leaf scratch
     int gp_ctas = 0;
+    DevBuf bgkl_long_units, bgkl_chunk_unit, bgkl_partial, bgkl_long_cnt;   // BGKLOctoMap: long neighbour lists cut into chunks
     DevBuf ray_of, rays, segs, seg_start;   // BGKLOctoMap: ray of each marker, ray segments, per-block training lists
     DevBuf lv_range, lv_info, ray_first, lv_qgrid, lv_active, lv_blk_slot, lv_blk_flags;   // BGKLVOctoMap
     DevBuf fz_vcnt, fz_bits, fz_wpre, fz_cell_cnt, fz_extra, fz_tsum, fz_newsums, fz_bsum, fz_long;   // sort-free front-end (frontend_fused.cu)
@@ -133,6 +134,7 @@ struct Map {
     void enqueue_gp_mv_tc(unsigned int t0, unsigned int chunk);
     void enqueue_peer_wait();
     bool ensure_fused_workspace();
+    bool ensure_bgkl_workspace();
     bool fused_applicable(int mode) const;
     void enqueue_fused_begin(int reset_counters);
     void enqueue_fused(int stage);

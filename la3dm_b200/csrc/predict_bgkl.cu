@@ -134,6 +134,50 @@ __device__ __forceinline__ float seg_dist_scaled(float qx, float qy, float qz, c
     return d / ell;
 }
 
+constexpr unsigned int kLongSegs = 192;     // neighbour lists longer than this are cut into chunks of kSegChunk segments
+constexpr unsigned int kSegChunk = 128;
+
+// segments [begin, end) of one neighbour list added to this lane's (ybar, kbar) in list order: tiles of 32 staged in shared
+// memory, culled against the box of the block's leaf centres
+__device__ __forceinline__ void seg_accumulate(SegSmem &S, const float4 *__restrict__ src, unsigned int begin, unsigned int end,
+                                               int node, float qx, float qy, float qz, float cx, float cy, float cz,
+                                               float reach, float cull2, float ell, float sf2, int lane, float &yb, float &kb) {
+    for (unsigned int base = begin; base < end; base += kSegTile) {
+        const unsigned int m = min((unsigned int) kSegTile, end - base);
+        bool keep = false;
+        float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sv = sa, sb = sa;
+        if ((unsigned int) lane < m) {
+            sa = src[2 * (size_t) (base + lane)];
+            sb = src[2 * (size_t) (base + lane) + 1];
+            sv = make_float4(sb.x - sa.x, sb.y - sa.y, sb.z - sa.z, 0.f);
+            const float c2 = sv.x * sv.x + sv.y * sv.y + sv.z * sv.z;
+            const float len = (float) sqrt((double) c2);
+            sv.w = len < 0.0001f ? -1.0f : c2;                     // EPSILON (bgklinference.h:14)
+            // cull: distance between the segment's bounding box and the box of the block's leaf centres
+            const float gx = fmaxf(fmaxf(fminf(sa.x, sb.x) - (cx + reach), (cx - reach) - fmaxf(sa.x, sb.x)), 0.f);
+            const float gy = fmaxf(fmaxf(fminf(sa.y, sb.y) - (cy + reach), (cy - reach) - fmaxf(sa.y, sb.y)), 0.f);
+            const float gz = fmaxf(fmaxf(fminf(sa.z, sb.z) - (cz + reach), (cz - reach) - fmaxf(sa.z, sb.z)), 0.f);
+            keep = gx * gx + gy * gy + gz * gz < cull2;
+        }
+        unsigned int todo = __ballot_sync(0xffffffffu, keep);
+        if (!todo) continue;
+        __syncwarp();
+        S.a[lane] = sa;
+        S.v[lane] = sv;
+        S.b[lane] = sb;
+        __syncwarp();
+        while (todo) {
+            const int q = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (node >= 0) {
+                const float4 za = S.a[q], zv = S.v[q], zb = S.b[q];
+                const float d = seg_dist_scaled(qx, qy, qz, za, zv, zb, ell);
+                if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb += k * za.w; kb += k; }
+            }
+        }
+    }
+}
+
 // test blocks per (k_bgkl_yk, k_bgkl_apply) pair: bounds the (ybar, kbar) buffer at 7 x leaves x 8 B per block
 inline unsigned int bgkl_chunk(const DevParams &P) {
     const unsigned int groups = (unsigned int) (P.finest + 31) / 32;
@@ -150,7 +194,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_bgkl_yk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ segs, const long long *__restrict__ keys,
           const unsigned char *__restrict__ pool, const float3 *__restrict__ lut, const DevParams *__restrict__ Pg,
           const ScanArgs *__restrict__ A, const ScanCounters *__restrict__ cnt, unsigned int t0, unsigned int chunk,
-          float2 *yk) {
+          float2 *yk, unsigned int *long_cnt, uint4 *long_units, unsigned int *chunk_unit, unsigned int long_cap,
+          unsigned int chunk_cap) {
     __shared__ SegSmem sm[kWarpsPerCta];
     __shared__ DevParams Ps;
     load_params(Ps, Pg);
@@ -199,42 +244,109 @@ k_bgkl_yk(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ seg
             qx = o.x + cx; qy = o.y + cy; qz = o.z + cz;           // Block::get_loc
         }
         const float4 *src = segs + 2 * (size_t) pl->start[nb];
-        float yb = 0.f, kb = 0.f;
-        for (unsigned int base = 0; base < n; base += kSegTile) {
-            const unsigned int m = min((unsigned int) kSegTile, n - base);
-            bool keep = false;
-            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sv = sa, sb = sa;
-            if ((unsigned int) lane < m) {
-                sa = src[2 * (size_t) (base + lane)];
-                sb = src[2 * (size_t) (base + lane) + 1];
-                sv = make_float4(sb.x - sa.x, sb.y - sa.y, sb.z - sa.z, 0.f);
-                const float c2 = sv.x * sv.x + sv.y * sv.y + sv.z * sv.z;
-                const float len = (float) sqrt((double) c2);
-                sv.w = len < 0.0001f ? -1.0f : c2;                     // EPSILON (bgklinference.h:14)
-                // cull: distance between the segment's bounding box and the box of the block's leaf centres
-                const float gx = fmaxf(fmaxf(fminf(sa.x, sb.x) - (cx + reach), (cx - reach) - fmaxf(sa.x, sb.x)), 0.f);
-                const float gy = fmaxf(fmaxf(fminf(sa.y, sb.y) - (cy + reach), (cy - reach) - fmaxf(sa.y, sb.y)), 0.f);
-                const float gz = fmaxf(fmaxf(fminf(sa.z, sb.z) - (cz + reach), (cz - reach) - fmaxf(sa.z, sb.z)), 0.f);
-                keep = gx * gx + gy * gy + gz * gz < cull2;
+        if (n > kLongSegs && long_cnt) {
+            // a list this long (the block around the sensor holds a marker of EVERY ray) is cut into chunks that other
+            // warps sum (k_bgkl_yk_long); the partial sums are added in chunk order (k_bgkl_yk_sum)
+            const unsigned int nch = (n + kSegChunk - 1u) / kSegChunk;
+            unsigned int first = 0, slot = 0;
+            if (lane == 0) {
+                slot = atomicAdd(&long_cnt[0], 1u);
+                first = atomicAdd(&long_cnt[1], nch);
             }
-            unsigned int todo = __ballot_sync(0xffffffffu, keep);
-            if (!todo) continue;
-            __syncwarp();
-            S.a[lane] = sa;
-            S.v[lane] = sv;
-            S.b[lane] = sb;
-            __syncwarp();
-            while (todo) {
-                const int q = __ffs(todo) - 1;
-                todo &= todo - 1;
-                if (node >= 0) {
-                    const float4 za = S.a[q], zv = S.v[q], zb = S.b[q];
-                    const float d = seg_dist_scaled(qx, qy, qz, za, zv, zb, ell);
-                    if (d < 1.0f) { const float k = sparse_kernel(d, sf2); yb += k * za.w; kb += k; }
-                }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            const bool fits = slot < long_cap && first + nch <= chunk_cap;
+            if (slot < long_cap && lane == 0) long_units[slot] = fits ? make_uint4(u, first, nch, 0u) : make_uint4(u, 0u, 0u, 0u);
+            for (unsigned int q = lane; q < nch; q += 32)
+                if (first + q < chunk_cap) chunk_unit[first + q] = fits ? slot : 0xFFFFFFFFu;
+            if (fits) continue;
+            // (no room in the lists -- they are sized for 7 x groups x memberships: summed right here, in one piece)
+        }
+        float yb = 0.f, kb = 0.f;
+        seg_accumulate(S, src, 0u, n, node, qx, qy, qz, cx, cy, cz, reach, cull2, ell, sf2, lane, yb, kb);
+        if (node >= 0) yk[((size_t) (t - t0) * 7 + nb) * (size_t) (groups * 32) + j] = make_float2(yb, kb);
+    }
+}
+
+// one warp per chunk of a long neighbour list: partial (ybar, kbar) of the unit's 32 leaves over kSegChunk segments
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_bgkl_yk_long(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ segs, const long long *__restrict__ keys,
+               const unsigned char *__restrict__ pool, const float3 *__restrict__ lut, const DevParams *__restrict__ Pg,
+               const ScanCounters *__restrict__ cnt, unsigned int t0, const unsigned int *__restrict__ long_cnt,
+               const uint4 *__restrict__ long_units, const unsigned int *__restrict__ chunk_unit, unsigned int long_cap,
+               unsigned int chunk_cap, float2 *partial) {
+    __shared__ SegSmem sm[kWarpsPerCta];
+    __shared__ DevParams Ps;
+    load_params(Ps, Pg);
+    if (cnt->overflow) return;
+    const DevParams &P = Ps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SegSmem &S = sm[warp];
+    const unsigned int n_chunks = min(long_cnt[1], chunk_cap);
+    const unsigned int gw = blockIdx.x * kWarpsPerCta + warp, n_w = gridDim.x * kWarpsPerCta;
+    const float ell = P.ell, sf2 = P.sf2, bs = P.block_size;
+    const unsigned int groups = (unsigned int) (P.finest + 31) / 32, per_block = 7u * groups;
+    const int pruned = P.pruned_state;
+    const float reach = 0.5f * (bs - P.resolution) * 1.001f;
+    const float cull2 = ell * ell * (1.0f + 1e-3f);
+    for (unsigned int ci = gw; ci < n_chunks; ci += n_w) {
+        const unsigned int slot_u = chunk_unit[ci];
+        if (slot_u >= long_cap) continue;
+        const uint4 lu = long_units[slot_u];
+        const unsigned int u = lu.x, c = ci - lu.y;
+        const unsigned int t = t0 + u / per_block, r = u % per_block;
+        const int nb = (int) (r / groups), s = (int) (r % groups);
+        const NeighbourPlan *pl = plan + t;
+        const unsigned int n = pl->count[nb];
+        const unsigned int slot = pl->slot;
+        int node = -1;
+        const int j = lane + 32 * s;
+        if (j < P.finest) {
+            if (pl->is_new) node = P.layer_off[P.depth - 1] + j;
+            else {
+                const unsigned char *rst = pool + (size_t) slot * (size_t) P.rec_bytes + P.st_off;
+                int d = P.depth - 1, i = j, shift = 0;
+                while (d > 0 && (rst[P.layer_off[d] + i] & 7) == pruned) { --d; i >>= 3; shift += 3; }
+                if (((i << shift) == j) && ((rst[P.layer_off[d] + i] & 7) != pruned)) node = P.layer_off[d] + i;
             }
         }
-        if (node >= 0) yk[((size_t) (t - t0) * 7 + nb) * (size_t) (groups * 32) + j] = make_float2(yb, kb);
+        const long long key = keys[slot];
+        const float cx = axis_center(key >> 40, bs), cy = axis_center((key >> 20) & 0xFFFFF, bs),
+                    cz = axis_center(key & 0xFFFFF, bs);
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (node >= 0) {
+            const float3 o = lut[node];
+            qx = o.x + cx; qy = o.y + cy; qz = o.z + cz;           // Block::get_loc
+        }
+        float yb = 0.f, kb = 0.f;
+        if (__any_sync(0xffffffffu, node >= 0))
+            seg_accumulate(S, segs + 2 * (size_t) pl->start[nb], c * kSegChunk, min(n, (c + 1u) * kSegChunk), node, qx, qy,
+                           qz, cx, cy, cz, reach, cull2, ell, sf2, lane, yb, kb);
+        partial[(size_t) ci * 32 + lane] = make_float2(yb, kb);
+    }
+}
+
+// (ybar, kbar) of a long unit = its chunks' partial sums added in chunk order; a lane per leaf, a warp per unit
+__global__ void k_bgkl_yk_sum(const DevParams *__restrict__ Pg, const ScanCounters *__restrict__ cnt, unsigned int t0,
+                              const unsigned int *__restrict__ long_cnt, const uint4 *__restrict__ long_units,
+                              unsigned int long_cap, const float2 *__restrict__ partial, float2 *yk) {
+    if (cnt->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_w = (gridDim.x * blockDim.x) >> 5;
+    const unsigned int n_units = min(long_cnt[0], long_cap);
+    const unsigned int groups = (unsigned int) (Pg->finest + 31) / 32, per_block = 7u * groups;
+    for (unsigned int q = gw; q < n_units; q += n_w) {
+        const uint4 lu = long_units[q];
+        if (lu.z == 0u) continue;
+        float yb = 0.f, kb = 0.f;
+        for (unsigned int c = 0; c < lu.z; ++c) {
+            const float2 p = partial[(size_t) (lu.y + c) * 32 + lane];
+            yb += p.x; kb += p.y;
+        }
+        const unsigned int tl = lu.x / per_block, r = lu.x % per_block;
+        const unsigned int nb = r / groups, s = r % groups;
+        const unsigned int j = (unsigned int) lane + 32u * s;
+        if (j < (unsigned int) Pg->finest) yk[((size_t) tl * 7 + nb) * (size_t) (groups * 32) + j] = make_float2(yb, kb);
     }
 }
 
@@ -322,6 +434,20 @@ k_bgkl_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__
 
 }  // namespace
 
+// long-list buffers of the predict stage for the current capacities (ensure_workspace)
+bool Map::ensure_bgkl_workspace() {
+    const size_t groups = (size_t) (hp.finest + 31) / 32;
+    const unsigned int chunk = bgkl_chunk(hp);
+    const size_t long_cap = 7 * groups * (size_t) caps.members / kLongSegs + 64;
+    const size_t chunk_cap = 7 * groups * (size_t) caps.members / kSegChunk + long_cap + 64;
+    const size_t iters = (size_t) caps.tests / chunk + 2;
+    bool moved = bgkl_long_units.reserve(long_cap * sizeof(uint4), stream);
+    moved |= bgkl_chunk_unit.reserve(chunk_cap * 4, stream);
+    moved |= bgkl_partial.reserve(chunk_cap * 32 * sizeof(float2), stream);
+    moved |= bgkl_long_cnt.reserve(iters * 8, stream);
+    return moved;
+}
+
 // per-block training lists (after the memberships were sorted by block: engine's binning stage)
 void Map::enqueue_bgkl_lists(const unsigned int *sorted_keys, const unsigned int *sorted_vals) {
     const int m_tiles = ceil_div(caps.members, kTile);
@@ -341,14 +467,34 @@ void Map::enqueue_predict_bgkl() {
     const size_t rec_smem = (size_t) hp.rec_bytes * kWarpsPerCta;
     const int staged = rec_smem <= 40 * 1024 ? 1 : 0;          // block_depth <= 4 (5.3 KB per record)
     record_event(ev_p0);
-    for (unsigned int t0 = 0; t0 < caps.tests; t0 += chunk) {
+    // long neighbour lists: units, chunks and partial sums (sized for every membership in 7 x groups lists)
+    const size_t groups = (size_t) (hp.finest + 31) / 32;
+    const size_t long_cap = 7 * groups * (size_t) caps.members / kLongSegs + 64;
+    const size_t chunk_cap = 7 * groups * (size_t) caps.members / kSegChunk + long_cap + 64;
+    const size_t iters = (size_t) caps.tests / chunk + 2;
+    if (bgkl_long_units.reserve(long_cap * sizeof(uint4), stream) | bgkl_chunk_unit.reserve(chunk_cap * 4, stream) |
+        bgkl_partial.reserve(chunk_cap * 32 * sizeof(float2), stream) | bgkl_long_cnt.reserve(iters * 8, stream))
+        throw StatusError{LA3DM_ERR_CUDA, "BGKL long-list buffers must be sized by ensure_workspace"};
+    LA3DM_CUDA(cudaMemsetAsync(bgkl_long_cnt.p, 0, iters * 8, stream));
+    unsigned int it = 0;
+    for (unsigned int t0 = 0; t0 < caps.tests; t0 += chunk, ++it) {
+        unsigned int *lc = bgkl_long_cnt.as<unsigned int>() + 2 * it;
         k_bgkl_yk<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), segs.as<float4>(),
                                                           keys.as<long long>(), pool.as<unsigned char>(), d_lut, d_params,
-                                                          d_args, d_cnt, t0, chunk, gp_mv.as<float2>());
+                                                          d_args, d_cnt, t0, chunk, gp_mv.as<float2>(), lc,
+                                                          bgkl_long_units.as<uint4>(), bgkl_chunk_unit.as<unsigned int>(),
+                                                          (unsigned int) long_cap, (unsigned int) chunk_cap);
+        k_bgkl_yk_long<<<ctas, kWarpsPerCta * 32, 0, stream>>>(plan.as<NeighbourPlan>(), segs.as<float4>(),
+                                                               keys.as<long long>(), pool.as<unsigned char>(), d_lut,
+                                                               d_params, d_cnt, t0, lc, bgkl_long_units.as<uint4>(),
+                                                               bgkl_chunk_unit.as<unsigned int>(), (unsigned int) long_cap,
+                                                               (unsigned int) chunk_cap, bgkl_partial.as<float2>());
+        k_bgkl_yk_sum<<<num_sms, 256, 0, stream>>>(d_params, d_cnt, t0, lc, bgkl_long_units.as<uint4>(),
+                                                   (unsigned int) long_cap, bgkl_partial.as<float2>(), gp_mv.as<float2>());
         k_bgkl_apply<<<ctas, kWarpsPerCta * 32, staged ? rec_smem : 0, stream>>>(
             plan.as<NeighbourPlan>(), pool.as<unsigned char>(), d_params, d_args, d_cnt, t0, chunk, gp_mv.as<float2>(),
             staged);
-        launches += 2;
+        launches += 4;
     }
     record_event(ev_p1);
 }
