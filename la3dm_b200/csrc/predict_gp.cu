@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kGpWarps = 4;           // warps per CTA in both kernels
 constexpr int kGpSmemN = 64;          // k_gp_train factorises blocks of up to this many points in shared memory
+constexpr int kGpWarpN = 32;          // ... and leaves the blocks above this size (up to kGpBigN) to k_gp_train_big
 
 // floats of factor storage per data block: packed lower triangle of L, then alpha
 __global__ void k_gp_sizes(const unsigned int *__restrict__ db_start, const ScanCounters *__restrict__ c,
@@ -45,11 +46,37 @@ __global__ void k_gp_check(const unsigned long long *__restrict__ off, const uns
     if (total > store_cap) atomicOr(&c->overflow, OVF_GPSTORE);
 }
 
+// Backward substitution alpha = L^-T z in place, by one warp: s = alpha_i - sum_{k > i, ascending} L_ki alpha_k, / L_ii.
+// The order of the subtractions is the scalar one; what the lanes share is everything else: the products L_ki alpha_k of 32
+// terms are formed in parallel (a lane each, rounded once like the scalar product) and handed round by shuffles, so the
+// dependent chain is one subtraction per term instead of an address computation, two loads, a product and a subtraction.
+__device__ __forceinline__ void gp_backward_warp(const float *L, float *alpha, unsigned int n, int lane) {
+    for (unsigned int ii = n; ii-- > 0;) {
+        float s = alpha[ii];
+        for (unsigned int k0 = ii + 1; k0 < n; k0 += 32) {
+            const unsigned int k = k0 + (unsigned int) lane;
+            float p = 0.f;
+            if (k < n) p = L[(size_t) k * (k + 1) / 2 + ii] * alpha[k];
+            const unsigned int cnt = min(32u, n - k0);
+            if (cnt == 32u) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) s -= __shfl_sync(0xffffffffu, p, q);
+            } else {
+                for (unsigned int q = 0; q < cnt; ++q) s -= __shfl_sync(0xffffffffu, p, (int) q);
+            }
+        }
+        s = s / L[(size_t) ii * (ii + 1) / 2 + ii];
+        __syncwarp();
+        if (lane == 0) alpha[ii] = s;
+        __syncwarp();
+    }
+}
+
 // GPRegressor::train, one warp per data block
 __global__ void __launch_bounds__(kGpWarps * 32)
 k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_start,
            const unsigned long long *__restrict__ off, float *store, const DevParams *__restrict__ Pg,
-           const ScanCounters *__restrict__ c) {
+           const ScanCounters *__restrict__ c, unsigned int big_max) {
     __shared__ float sL[kGpWarps][kGpSmemN * (kGpSmemN + 1) / 2 + kGpSmemN];
     if (c->overflow) return;
     const int lane = threadIdx.x & 31;
@@ -58,6 +85,7 @@ k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_s
     const unsigned int D = c->n_data_blocks;
     for (unsigned int d = gw; d < D; d += n_w) {
         const unsigned int first = db_start[d], n = db_start[d + 1] - first;
+        if (n > (unsigned int) kGpWarpN && n <= big_max) continue;      // k_gp_train_big's
         const float4 *x = pts + first;
         float *Lg = store + off[d];                      // L[i][j] at i (i + 1) / 2 + j, then alpha
         // a block of up to kGpSmemN points is factorised in shared memory (the column sweeps are chains of dependent
@@ -117,32 +145,95 @@ k_gp_train(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_s
             for (unsigned int i = k + 1 + lane; i < n; i += 32) alpha[i] -= L[(size_t) i * (i + 1) / 2 + k] * ak;
             __syncwarp();
         }
-        // Backward: s = alpha_i - sum_{k > i, ascending} L_ki alpha_k needs every later alpha first: one lane
-        // (the loads of eight terms are issued together, the subtractions stay one after the other in ascending k)
-        if (lane == 0) {
-            for (unsigned int ii = n; ii-- > 0;) {
-                float s = alpha[ii];
-                unsigned int k = ii + 1;
-                for (; k + 8 <= n; k += 8) {
-                    float l[8], a8[8];
-#pragma unroll
-                    for (unsigned int q = 0; q < 8; ++q) {
-                        l[q] = L[(size_t) (k + q) * (k + q + 1) / 2 + ii];
-                        a8[q] = alpha[k + q];
-                    }
-#pragma unroll
-                    for (unsigned int q = 0; q < 8; ++q) s -= l[q] * a8[q];
-                }
-                for (; k < n; ++k) s -= L[(size_t) k * (k + 1) / 2 + ii] * alpha[k];
-                alpha[ii] = s / L[(size_t) ii * (ii + 1) / 2 + ii];
-            }
-        }
+        // Backward: s = alpha_i - sum_{k > i, ascending} L_ki alpha_k needs every later alpha first
+        gp_backward_warp(L, alpha, n, lane);
         __syncwarp();
         if (staged) {
             const unsigned int words = n * (n + 1) / 2 + n;
             for (unsigned int w = lane; w < words; w += 32) Lg[w] = L[w];
             __syncwarp();
         }
+    }
+}
+
+
+// GPRegressor::train for the data blocks of more than kGpWarpN points (up to kGpBigN): a CTA per block, the factor in
+// shared memory, a thread per row.  Every element's sum runs in ascending k exactly like k_gp_train (same results, bit
+// for bit); what changes is that the rows of a column are computed by 256 threads instead of 32 lanes, out of shared
+// memory instead of L2 -- left to one warp these few blocks outlast the rest of the scan's training.
+constexpr int kGpBigN = 224;
+constexpr int kGpBigThreads = 256;
+constexpr size_t kGpBigSmem = ((size_t) kGpBigN * (kGpBigN + 1) / 2 + kGpBigN) * sizeof(float);
+
+__global__ void __launch_bounds__(kGpBigThreads)
+k_gp_train_big(const float4 *__restrict__ pts, const unsigned int *__restrict__ db_start,
+               const unsigned long long *__restrict__ off, float *store, const DevParams *__restrict__ Pg,
+               const ScanCounters *__restrict__ c) {
+    extern __shared__ __align__(16) float gp_big_smem[];
+    __shared__ float s_ljj;
+    if (c->overflow) return;
+    const float sf2 = Pg->sf2, noise = Pg->noise;
+    const unsigned int D = c->n_data_blocks;
+    const unsigned int tid = threadIdx.x;
+    for (unsigned int d = blockIdx.x; d < D; d += gridDim.x) {
+        const unsigned int first = db_start[d], n = db_start[d + 1] - first;
+        if (n <= (unsigned int) kGpWarpN || n > (unsigned int) kGpBigN) continue;
+        const float4 *x = pts + first;
+        float *Lg = store + off[d];
+        float *L = gp_big_smem;
+        float *alpha = L + (size_t) n * (n + 1) / 2;
+        __syncthreads();
+        // K + noise I, lower triangle (:44-46)
+        const unsigned int tri = n * (n + 1) / 2;
+        for (unsigned int e = tid; e < tri; e += kGpBigThreads) {
+            // (i, j) of the packed index e: i = floor((sqrt(8 e + 1) - 1) / 2), corrected for rounding
+            unsigned int i = (unsigned int) ((sqrtf(8.0f * (float) e + 1.0f) - 1.0f) * 0.5f);
+            while (i * (i + 1) / 2 > e) --i;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            const unsigned int j = e - i * (i + 1) / 2;
+            const float4 xi = x[i], xj = x[j];
+            float k = matern3(xi.x, xi.y, xi.z, xj.x, xj.y, xj.z, sf2);
+            if (i == j) k = k + noise * 1.0f;
+            L[e] = k;
+        }
+        __syncthreads();
+        // Cholesky (LLT, :47): column by column, a thread per row; each element's sum runs in ascending k
+        for (unsigned int j = 0; j < n; ++j) {
+            const float *rj = L + (size_t) j * (j + 1) / 2;
+            const unsigned int i = j + tid;
+            float s = 0.f;
+            float *ri = nullptr;
+            if (i < n) {
+                ri = L + (size_t) i * (i + 1) / 2;
+                s = ri[j];
+                unsigned int k = 0;
+                for (; k + 4 <= j; k += 4) {
+                    const float a0 = ri[k], a1 = ri[k + 1], a2 = ri[k + 2], a3 = ri[k + 3];
+                    const float b0 = rj[k], b1 = rj[k + 1], b2 = rj[k + 2], b3 = rj[k + 3];
+                    s -= a0 * b0; s -= a1 * b1; s -= a2 * b2; s -= a3 * b3;
+                }
+                for (; k < j; ++k) s -= ri[k] * rj[k];
+            }
+            if (tid == 0) { s = sqrtf(s); s_ljj = s; }
+            __syncthreads();                 // the diagonal is known; every read of row j's old elements is done
+            if (i < n) ri[j] = tid == 0 ? s : s / s_ljj;
+            __syncthreads();
+        }
+        // alpha = L^-T (L^-1 y) (:48-49).  Forward: column oriented, every s_i is reduced in ascending k.
+        for (unsigned int i = tid; i < n; i += kGpBigThreads) alpha[i] = x[i].w;
+        __syncthreads();
+        for (unsigned int k = 0; k < n; ++k) {
+            if (tid == 0) alpha[k] = alpha[k] / L[(size_t) k * (k + 1) / 2 + k];
+            __syncthreads();
+            const float ak = alpha[k];
+            const unsigned int i = k + 1 + tid;
+            if (i < n) alpha[i] -= L[(size_t) i * (i + 1) / 2 + k] * ak;
+            __syncthreads();
+        }
+        // Backward: s = alpha_i - sum_{k > i, ascending} L_ki alpha_k needs every later alpha first: one warp
+        if (tid < 32) gp_backward_warp(L, alpha, n, (int) tid);
+        __syncthreads();
+        for (unsigned int w = tid; w < tri + n; w += kGpBigThreads) Lg[w] = L[w];
     }
 }
 
@@ -361,8 +452,19 @@ void Map::enqueue_gp() {
     const unsigned long long *off = gp_off.as<unsigned long long>();
     const int ctas = num_sms * 4;
     record_event(ev_p0);
+    // the few big data blocks first (a CTA each, they are the long poles), then everything else (a warp each)
+    {
+        static bool attr_done[64] = {};
+        if (device < 64 && !attr_done[device]) {
+            LA3DM_CUDA(cudaFuncSetAttribute(k_gp_train_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kGpBigSmem));
+            attr_done[device] = true;
+        }
+    }
+    k_gp_train_big<<<num_sms, kGpBigThreads, kGpBigSmem, stream>>>(pts_sorted.as<float4>(), db_start.as<unsigned int>(), off,
+                                                                  gp_store.as<float>(), d_params, d_cnt);
     k_gp_train<<<ctas, kGpWarps * 32, 0, stream>>>(pts_sorted.as<float4>(), db_start.as<unsigned int>(), off,
-                                                   gp_store.as<float>(), d_params, d_cnt);
+                                                   gp_store.as<float>(), d_params, d_cnt, (unsigned int) kGpBigN);
+    ++launches;
     // predict: (mean, variance) of every (test block, neighbour, leaf) in parallel, then the sequential fusion per block
     const unsigned int chunk = gp_chunk(hp);
     const size_t apply_smem = (size_t) hp.rec_bytes * kGpWarps;
