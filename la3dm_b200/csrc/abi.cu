@@ -75,6 +75,9 @@ int la3dm_create(int method, const la3dm_params *params, int device, la3dm_map *
 int la3dm_destroy(la3dm_map *map) {
     if (!map) return LA3DM_ERR_INVALID;
     cudaSetDevice(map->m.device);
+    if (map->m.peer_wait_pending) {          // peers may still be storing into this replica's pool
+        try { map->m.peer_wait_now(); } catch (...) { cudaGetLastError(); }
+    }
     if (map->m.stream) cudaStreamSynchronize(map->m.stream);
     delete map;
     return LA3DM_OK;

@@ -486,7 +486,12 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
     }
 
     dump_fused_trace();
-    if (!frontend_only) { ++scan_seq; if (peers_attached && peers_deferred) peers_unsynced = true; }
+    if (!frontend_only) {
+        ++scan_seq;
+        if (peers_attached && peers_deferred) peers_unsynced = true;
+        static const bool wait_in_scan = getenv("LA3DM_PEER_WAIT_IN_SCAN") != nullptr;
+        if (peers_attached && !peers_deferred && !wait_in_scan) peer_wait_pending = true;
+    }
     // blocks after the scan = blocks before + blocks k_plan / k_lv_blocks created (no overflow on this path)
     n_blocks = frontend_only ? n_blocks : (long long) h_args->n_blocks + (long long) h_cnt->n_new_blocks;
     last_T = frontend_only ? 0 : h_cnt->n_test_blocks;

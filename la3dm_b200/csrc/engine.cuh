@@ -89,6 +89,7 @@ struct Map {
     PeerTable h_peers{};
     PeerTable *d_peers = nullptr;
     DevBuf peer_flags;              // [kMaxPeers] u64, written by the peers
+    bool peer_wait_pending = false;    // eager mode: scans whose peer stores have not been waited for yet
     bool peers_share_device = false;   // a peer replica lives on this very device (single-GPU tests)
     bool peers_attached = false, peers_deferred = false, peers_unsynced = false;
     DevBuf touched;                 // [pool_cap] bytes: block was a test block of a scan since the last la3dm_export_touched(clear)
@@ -141,6 +142,7 @@ struct Map {
     void dump_fused_trace();
     void peer_sync();
     void check_synced() const;
+    void peer_wait_now();
     // export
     void export_blocks(int64_t *keys, la3dm_node *nodes, size_t cap, size_t *n);
     long long count_leaves();

@@ -1381,18 +1381,35 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
                     if (p != my_rank) reinterpret_cast<uint4 *>(PT->pool[p] + rec_off)[w] = v;
             }
         }
-        if (!valid) continue;
-        F.touched[pl.slot] = 1;                // read side: la3dm_export_touched
-        if (F.cell_test) F.cell_test[tid_cell] = t + 1;
-        if (F.heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank) {
-            if (totp > kMegaTot) {
+        // this rank's work lists; one atomic per warp and list (every test block of the scan passes here: 10^5 atomics on
+        // one counter would serialise in L2)
+        {
+            const bool own = valid && F.heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank;
+            const bool mega = own && totp > kMegaTot;
+            const bool heavy = own && !mega && totp > A->heavy_tot;
+            const bool light = own && !mega && !heavy && A->shard_world > 1;     // (one rank: walked in cell order)
+            const int lane = threadIdx.x & 31;
+            const unsigned int lt = (1u << lane) - 1u;
+            const unsigned int mh = __ballot_sync(0xffffffffu, heavy), ml = __ballot_sync(0xffffffffu, light);
+            unsigned int bh = 0, bl = 0;
+            if (lane == 0) {
+                if (mh) bh = atomicAdd(&c->n_heavy, (unsigned int) __popc(mh));
+                if (ml) bl = atomicAdd(&c->n_light, (unsigned int) __popc(ml));
+            }
+            bh = __shfl_sync(0xffffffffu, bh, 0);
+            bl = __shfl_sync(0xffffffffu, bl, 0);
+            if (heavy) F.heavy_list[bh + __popc(mh & lt)] = t;
+            if (light) F.light_list[bl + __popc(ml & lt)] = t;
+            if (mega) {                    // cut into chunks, each predicted as a unit of its own (predict_bgk.cu)
                 const unsigned int nch = (totp + kMegaChunkPts - 1u) / kMegaChunkPts;
                 const unsigned int first = atomicAdd(&c->n_mega_chunks, nch), m = atomicAdd(&c->n_mega, 1u);
                 F.mega_list[m] = make_uint4(t, first, nch, 0u);
                 for (unsigned int q = 0; q < nch; ++q) F.chunk_mega[first + q] = m;
-            } else if (totp > A->heavy_tot) F.heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
-            else if (A->shard_world > 1) F.light_list[atomicAdd(&c->n_light, 1u)] = t;
+            }
         }
+        if (!valid) continue;
+        F.touched[pl.slot] = 1;                // read side: la3dm_export_touched
+        if (F.cell_test) F.cell_test[tid_cell] = t + 1;
         uint4 *dst = reinterpret_cast<uint4 *>(F.plan + t);
         const uint4 *src = reinterpret_cast<const uint4 *>(&pl);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];

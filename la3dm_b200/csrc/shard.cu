@@ -6,6 +6,9 @@
 // the rows over NCCL/NVLink and every rank scatters the peers' rows into its replica.
 #include <cstring>
 
+#include <mutex>
+#include <set>
+
 #include "engine.cuh"
 
 namespace la3dm_b200 {
@@ -43,6 +46,20 @@ __global__ void k_peer_wait(const ScanArgs *__restrict__ A, ScanCounters *c, con
     const long long t0 = clock64();
     while (*f < want) {
         if (clock64() - t0 > 20000000000ll) { atomicOr(&c->overflow, OVF_PEER); break; }   // ~10 s
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// the same wait outside of a scan (read side): flags[p] >= want for every peer p
+__global__ void k_peer_wait_lazy(const PeerTable *__restrict__ PT, const unsigned long long *flags, unsigned long long want,
+                                 unsigned int *timed_out) {
+    const int p = threadIdx.x;
+    if (p >= PT->world || p == PT->rank) return;
+    const volatile unsigned long long *f = flags + p;
+    const long long t0 = clock64();
+    while (*f < want) {
+        if (clock64() - t0 > 20000000000ll) { *timed_out = 1u; break; }   // ~10 s
         __nanosleep(200);
     }
     __threadfence_system();
@@ -102,6 +119,22 @@ void Map::check_synced() const {
     if (peers_attached && peers_deferred && peers_unsynced)
         throw StatusError{LA3DM_ERR_INVALID, "this replica holds only its own blocks' latest state: la3dm_peer_sync() "
                                              "(on every rank) before reading the map"};
+    // eager mode: the peers' stores of the last scans may still be on their way (see enqueue_peer_wait)
+    if (peer_wait_pending) const_cast<Map *>(this)->peer_wait_now();
+}
+
+// Blocks until every peer has flagged every scan up to scan_seq as pushed into this replica.
+void Map::peer_wait_now() {
+    if (!peers_attached || peers_deferred) { peer_wait_pending = false; return; }
+    LA3DM_CUDA(cudaSetDevice(device));
+    unsigned int *scratch = reinterpret_cast<unsigned int *>(peer_flags.as<unsigned long long>() + 2 * kMaxPeers);
+    LA3DM_CUDA(cudaMemsetAsync(scratch + 2, 0, 4, stream));
+    k_peer_wait_lazy<<<1, 32, 0, stream>>>(d_peers, peer_flags.as<unsigned long long>(), scan_seq, scratch + 2);
+    unsigned int timed_out = 0;
+    LA3DM_CUDA(cudaMemcpyAsync(&timed_out, scratch + 2, 4, cudaMemcpyDeviceToHost, stream));
+    LA3DM_CUDA(cudaStreamSynchronize(stream));
+    if (timed_out) throw StatusError{LA3DM_ERR_CUDA, "timed out waiting for a peer replica to finish its scans"};
+    peer_wait_pending = false;
 }
 
 // collective: every rank calls it; on return all replicas are identical
@@ -122,8 +155,14 @@ void Map::peer_sync() {
     peers_unsynced = false;
 }
 
+// Eager mode.  A rank only ever predicts -- reads and writes -- the blocks it owns, so the next scan does not depend on the
+// peers' stores of this one; only a READ of the map does.  By default the wait is therefore left to the read side
+// (check_synced: export, search, ray casting, save, detach) and the peers' stores overlap the next scan's front-end;
+// LA3DM_PEER_WAIT_IN_SCAN=1 waits at the end of every scan instead.
 void Map::enqueue_peer_wait() {
     if (!peers_attached || peers_deferred) return;
+    static const bool in_scan = getenv("LA3DM_PEER_WAIT_IN_SCAN") != nullptr;
+    if (!in_scan) return;
     k_peer_wait<<<1, 32, 0, stream>>>(d_args, d_cnt, peer_flags.as<unsigned long long>());
     ++launches;
 }
@@ -131,6 +170,9 @@ void Map::enqueue_peer_wait() {
 }  // namespace la3dm_b200
 
 using la3dm_b200::Map;
+
+static std::mutex g_ipc_mutex;
+static std::set<const void *> g_ipc_pools;      // pool bases obtained from la3dm_peer_ipc_open
 
 extern "C" {
 
@@ -171,7 +213,7 @@ static int ensure_peer_buffers(la3dm_map *map) {
     Map &m = map->m;
     if (cudaSetDevice(m.device) != cudaSuccess) return LA3DM_ERR_CUDA;
     if (!m.peer_flags.p) {
-        try { m.peer_flags.reserve((2 * la3dm_b200::kMaxPeers + 1) * sizeof(unsigned long long), m.stream); }
+        try { m.peer_flags.reserve((2 * la3dm_b200::kMaxPeers + 2) * sizeof(unsigned long long), m.stream); }
         catch (...) { return LA3DM_ERR_NOMEM; }
         cudaMemsetAsync(m.peer_flags.p, 0, m.peer_flags.cap, m.stream);
         cudaStreamSynchronize(m.stream);
@@ -223,6 +265,10 @@ int la3dm_peer_ipc_open(la3dm_map *map, const void *handle_pool, const void *han
     if (e != cudaSuccess) return peer_fail(map, "cudaIpcOpenMemHandle(pool)", e);
     e = cudaIpcOpenMemHandle(flags, hf_, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) return peer_fail(map, "cudaIpcOpenMemHandle(flags)", e);
+    {   // a pool opened through IPC belongs to another process (cudaPointerGetAttributes reports the MAPPING device for it)
+        std::lock_guard<std::mutex> lock(g_ipc_mutex);
+        g_ipc_pools.insert(*pool_base);
+    }
     return LA3DM_OK;
 }
 
@@ -251,6 +297,10 @@ int la3dm_peer_attach(la3dm_map *map, int world, int rank, void *const *pool_bas
     for (int p = 0; p < world; ++p) {
         if (p == rank) continue;
         cudaPointerAttributes at;
+        {
+            std::lock_guard<std::mutex> lock(g_ipc_mutex);
+            if (g_ipc_pools.count(pool_bases[p])) continue;                    // another process: its own device
+        }
         if (cudaPointerGetAttributes(&at, pool_bases[p]) == cudaSuccess) { if (at.device == m.device) m.peers_share_device = true; }
         else cudaGetLastError();
     }
@@ -279,6 +329,12 @@ int la3dm_peer_sync(la3dm_map *map) {
 int la3dm_peer_detach(la3dm_map *map) {
     if (!map) return LA3DM_ERR_INVALID;
     if (map->m.peers_unsynced) { map->m.last_error = "peer_detach: la3dm_peer_sync() first"; return LA3DM_ERR_INVALID; }
+    try {
+        if (map->m.peer_wait_pending) map->m.peer_wait_now();      // the peers' last stores must have landed
+    } catch (...) {
+        map->m.last_error = "peer_detach: timed out waiting for a peer replica";
+        return LA3DM_ERR_CUDA;
+    }
     map->m.peers_attached = false;
     map->m.shard_rank = 0;
     map->m.shard_world = 1;
