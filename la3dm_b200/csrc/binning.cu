@@ -438,40 +438,62 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
             }
         }
     }
-    if (!valid) return;
-    touched[pl.slot] = 1;                      // read side: la3dm_export_touched
-    if (cell_test) cell_test[test_id[t]] = t + 1;
-    const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
+    // Peers: a block that another rank owns only needs its slot here (every replica numbers the blocks alike); its
+    // neighbour ranges, its plan entry and its place in a work list are the owner's business.
+    const bool own = valid && (!A->peers || block_owner(key, t, A->shard_world, true) == A->shard_rank);
     unsigned int tot = 0;
-    const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
+    if (valid) touched[pl.slot] = 1;                      // read side: la3dm_export_touched
+    if (valid && cell_test) cell_test[test_id[t]] = t + 1;
+    if (own) {
+        const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
+        const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        const int xx = x + dx[k], yy = y + dy[k], zz = z + dz[k];
-        unsigned int start = 0, count = 0;
-        if (xx >= 0 && xx < nx && yy >= 0 && yy < ny && zz >= 0 && zz < nz) {
-            const unsigned int nid = ((unsigned int) xx * (unsigned int) ny + (unsigned int) yy) * (unsigned int) nz +
-                                     (unsigned int) zz;
-            const unsigned int d = cell_db[nid];
-            if (d) { start = db_start[d - 1]; count = db_start[d] - start; }
-            if (plan_db) plan_db[(size_t) t * 8 + k] = d;      // data block index + 1 (GP: locates the regressor)
-        } else if (plan_db) plan_db[(size_t) t * 8 + k] = 0;
-        pl.start[k] = start;
-        pl.count[k] = count;
-        tot += count;
+        for (int k = 0; k < 7; ++k) {
+            const int xx = x + dx[k], yy = y + dy[k], zz = z + dz[k];
+            unsigned int start = 0, count = 0;
+            if (xx >= 0 && xx < nx && yy >= 0 && yy < ny && zz >= 0 && zz < nz) {
+                const unsigned int nid = ((unsigned int) xx * (unsigned int) ny + (unsigned int) yy) * (unsigned int) nz +
+                                         (unsigned int) zz;
+                const unsigned int d = cell_db[nid];
+                if (d) { start = db_start[d - 1]; count = db_start[d] - start; }
+                if (plan_db) plan_db[(size_t) t * 8 + k] = d;      // data block index + 1 (GP: locates the regressor)
+            } else if (plan_db) plan_db[(size_t) t * 8 + k] = 0;
+            pl.start[k] = start;
+            pl.count[k] = count;
+            tot += count;
+        }
     }
-    // this rank's test blocks: the heavy ones (predicted first) and the rest
-    if (heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank) {
-        if (tot > kMegaTot) {              // cut into chunks, each predicted as a unit of its own (predict_bgk.cu)
+    // this rank's test blocks: the heavy ones (predicted first) and the rest; one atomic per warp and list (every test
+    // block of the scan passes here: millions of atomics on one counter serialise in L2)
+    {
+        const bool listed = own && heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank;
+        const bool mega = listed && tot > kMegaTot;
+        const bool heavy = listed && !mega && tot > A->heavy_tot;
+        const bool light = listed && !mega && !heavy && A->shard_world > 1;   // (one rank: walked in cell order)
+        const int lane = threadIdx.x & 31;
+        const unsigned int lt = (1u << lane) - 1u;
+        const unsigned int mh = __ballot_sync(0xffffffffu, heavy), ml = __ballot_sync(0xffffffffu, light);
+        unsigned int bh = 0, bl = 0;
+        if (lane == 0) {
+            if (mh) bh = atomicAdd(&c->n_heavy, (unsigned int) __popc(mh));
+            if (ml) bl = atomicAdd(&c->n_light, (unsigned int) __popc(ml));
+        }
+        bh = __shfl_sync(0xffffffffu, bh, 0);
+        bl = __shfl_sync(0xffffffffu, bl, 0);
+        if (heavy) heavy_list[bh + __popc(mh & lt)] = t;
+        if (light) light_list[bl + __popc(ml & lt)] = t;
+        if (mega) {                        // cut into chunks, each predicted as a unit of its own (predict_bgk.cu)
             const unsigned int nch = (tot + kMegaChunkPts - 1u) / kMegaChunkPts;
             const unsigned int first = atomicAdd(&c->n_mega_chunks, nch), m = atomicAdd(&c->n_mega, 1u);
             mega_list[m] = make_uint4(t, first, nch, 0u);
             for (unsigned int q = 0; q < nch; ++q) chunk_mega[first + q] = m;
-        } else if (tot > A->heavy_tot) heavy_list[atomicAdd(&c->n_heavy, 1u)] = t;
-        else if (A->shard_world > 1) light_list[atomicAdd(&c->n_light, 1u)] = t;   // (one rank: walked in cell order)
+        }
     }
+    if (!valid) return;
     uint4 *dst = reinterpret_cast<uint4 *>(plan + t);
     const uint4 *src = reinterpret_cast<const uint4 *>(&pl);
-    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    if (own) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+    dst[3] = src[3];                       // (count[5..6], slot, is_new)
 }
 
 __global__ void k_hash_clear(long long *hkeys, size_t n) {

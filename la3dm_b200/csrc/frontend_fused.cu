@@ -1318,7 +1318,9 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
         // the neighbour ranges first (their loads are in flight while the default records are written)
         const int nz = g->n[2], ny = g->n[1], nx = g->n[0];
         unsigned int totp = 0;
-        if (valid) {
+        // peers: a block that another rank owns only needs its slot here; ranges, plan entry and work lists are the owner's
+        const bool mine_blk = valid && (!A->peers || block_owner(key, t, A->shard_world, true) == A->shard_rank);
+        if (mine_blk) {
             const int dx[7] = {0, 1, -1, 0, 0, 0, 0}, dy[7] = {0, 0, 0, 1, -1, 0, 0}, dz[7] = {0, 0, 0, 0, 0, 1, -1};
             unsigned int dd[7];
 #pragma unroll
@@ -1384,7 +1386,7 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
         // this rank's work lists; one atomic per warp and list (every test block of the scan passes here: 10^5 atomics on
         // one counter would serialise in L2)
         {
-            const bool own = valid && F.heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank;
+            const bool own = mine_blk && F.heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank;
             const bool mega = own && totp > kMegaTot;
             const bool heavy = own && !mega && totp > A->heavy_tot;
             const bool light = own && !mega && !heavy && A->shard_world > 1;     // (one rank: walked in cell order)
@@ -1412,7 +1414,8 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
         if (F.cell_test) F.cell_test[tid_cell] = t + 1;
         uint4 *dst = reinterpret_cast<uint4 *>(F.plan + t);
         const uint4 *src = reinterpret_cast<const uint4 *>(&pl);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        if (mine_blk) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+        dst[3] = src[3];                   // (count[5..6], slot, is_new)
     }
 }
 
