@@ -155,8 +155,6 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     if (p.block_depth < 1 || p.block_depth > kMaxDepth) throw StatusError{LA3DM_ERR_INVALID, "block_depth out of range"};
     if (!(p.resolution > 0) || !(p.ell > 0)) throw StatusError{LA3DM_ERR_INVALID, "resolution and ell must be > 0"};
     // configurations the predict kernels do not cover are refused HERE, before any scan can touch the map
-    if (method == LA3DM_GP && p.block_depth > 4)
-        throw StatusError{LA3DM_ERR_UNSUPPORTED, "GPOctoMap: block_depth > 4 is not implemented"};
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

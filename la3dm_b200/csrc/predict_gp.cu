@@ -341,14 +341,16 @@ k_gp_mv(const NeighbourPlan *__restrict__ plan, const unsigned int *__restrict__
 __global__ void __launch_bounds__(kGpWarps * 32)
 k_gp_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ pool, const DevParams *__restrict__ Pg,
            const ScanArgs *__restrict__ A, ScanCounters *cnt, unsigned int t0, unsigned int chunk,
-           const float2 *__restrict__ mv) {
+           const float2 *__restrict__ mv, int staged) {
     extern __shared__ __align__(16) unsigned char gp_smem_raw[];
     __shared__ DevParams Ps;
     load_params(Ps, Pg);
     if (cnt->overflow) return;
     const DevParams &P = Ps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *srec = reinterpret_cast<uint4 *>(gp_smem_raw + (size_t) warp * P.rec_bytes);
+    // the record is staged in shared memory when it fits (block_depth <= 4: 5.3 KB), updated in place in global memory
+    // otherwise (42 KB at depth 5)
+    uint4 *smem_rec = reinterpret_cast<uint4 *>(gp_smem_raw + (size_t) warp * (staged ? P.rec_bytes : 0));
     const unsigned int T = cnt->n_test_blocks;
     if (t0 >= T) return;
     const unsigned int t1 = min(T, t0 + chunk);
@@ -356,16 +358,17 @@ k_gp_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ p
     const unsigned int shard_world = (unsigned int) A->shard_world, shard_rank = (unsigned int) A->shard_rank;
     const int groups = (P.finest + 31) / 32;
     const int pruned = P.pruned_state;
-    float2 *rab = reinterpret_cast<float2 *>(srec);
-    unsigned char *rst = reinterpret_cast<unsigned char *>(srec) + P.st_off;
     unsigned long long visits = 0, updates = 0, pairs = 0;
 
     for (unsigned int t = t0 + gw; t < t1; t += n_w) {
         if (t % shard_world != shard_rank) continue;
         const NeighbourPlan pl = plan[t];
         uint4 *grec = reinterpret_cast<uint4 *>(pool + (size_t) pl.slot * (size_t) P.rec_bytes);
+        uint4 *srec = staged ? smem_rec : grec;
+        float2 *rab = reinterpret_cast<float2 *>(srec);
+        unsigned char *rst = reinterpret_cast<unsigned char *>(srec) + P.st_off;
         __syncwarp();
-        stage_record(srec, grec, pl.is_new != 0, P, lane);
+        if (staged || pl.is_new) stage_record(srec, grec, pl.is_new != 0, P, lane);
         __syncwarp();
         unsigned int n_total = 0;
         for (int nb = 0; nb < 7; ++nb) n_total += pl.count[nb];
@@ -400,7 +403,7 @@ k_gp_apply(const NeighbourPlan *__restrict__ plan, unsigned char *__restrict__ p
         __syncwarp();
         if (dirty) {
             prune_record(rab, rst, P, lane);
-            for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = srec[w];
+            if (staged) for (int w = lane; w < (P.rec_bytes >> 4); w += 32) grec[w] = srec[w];
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -436,7 +439,6 @@ int gp_tc_max_n();   // predict_gp_tc.cu
 // storage offsets of the regressors and the capacity checks (runs before the map is touched)
 void Map::enqueue_gp_sizes() {
     // k_gp_apply stages a block record per warp in shared memory: 5.3 KB at depth 4, 42 KB at depth 5
-    if (hp.depth > 4) throw StatusError{LA3DM_ERR_UNSUPPORTED, "GPOctoMap: block_depth > 4 not supported on the GPU yet"};
     const unsigned int cap = caps.members;     // data blocks <= memberships
     const int grid = ceil_div(cap, 256);
     unsigned long long *sizes = gp_sizes.as<unsigned long long>(), *off = gp_off.as<unsigned long long>();
@@ -467,7 +469,9 @@ void Map::enqueue_gp() {
     ++launches;
     // predict: (mean, variance) of every (test block, neighbour, leaf) in parallel, then the sequential fusion per block
     const unsigned int chunk = gp_chunk(hp);
-    const size_t apply_smem = (size_t) hp.rec_bytes * kGpWarps;
+    const size_t rec_smem = (size_t) hp.rec_bytes * kGpWarps;
+    const int staged = rec_smem <= 40 * 1024 ? 1 : 0;          // block_depth <= 4 (5.3 KB per record)
+    const size_t apply_smem = staged ? rec_smem : 0;
     // regressors of up to gp_tc_max_n() points go through tcgen05.mma (block_depth <= 3: 64 finest leaves per block);
     // LA3DM_GP_SIMT=1 keeps everything on the scalar kernel (A/B, and the fallback if TMEM cannot be had)
     static const bool simt_only = getenv("LA3DM_GP_SIMT") != nullptr;
@@ -482,7 +486,7 @@ void Map::enqueue_gp() {
                                                        gp_mv.as<float2>(), tc_max_n);
         k_gp_apply<<<gp_ctas, kGpWarps * 32, apply_smem, stream>>>(plan.as<NeighbourPlan>(), pool.as<unsigned char>(),
                                                                    d_params, d_args, d_cnt, t0, chunk,
-                                                                   gp_mv.as<float2>());
+                                                                   gp_mv.as<float2>(), staged);
         launches += 2;
     }
     record_event(ev_p1);
