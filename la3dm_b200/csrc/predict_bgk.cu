@@ -251,7 +251,8 @@ __device__ __forceinline__ float sparse_kernel_d2(float d2, float sf2) {
 
 // kMode 0: whole blocks (heavy list, then light list); 1: the chunks of the mega blocks -> partial sums; 2: the mega
 // blocks are finished from their partial sums (also signals the peers: it is the last launch of the scan).
-template <bool kD3, int kMode>
+// kBulk: the A/B variant that stages the neighbour ranges with cp.async.bulk + mbarrier (LA3DM_PREDICT_BULK=1)
+template <bool kD3, int kMode, bool kBulk = false>
 __global__ void __launch_bounds__(kFlatWarps * 32, LA3DM_FLAT_MIN_CTAS)
 k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restrict__ pts,
                    const long long *__restrict__ keys, unsigned char *__restrict__ pool,
@@ -282,6 +283,21 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
     const unsigned int full = 0xffffffffu, lt = (1u << lane) - 1u;
     FlatSmem &S = sm[warp];
     unsigned char *sst = reinterpret_cast<unsigned char *>(S.st);
+    // bulk variant: 32 points staged per warp by the async proxy, completion on a per-warp mbarrier
+    float4 *bulk_stage = nullptr;
+    unsigned int bulk_stage_addr = 0, bulk_bar = 0, bulk_phase = 0;
+    if constexpr (kBulk) {
+        __shared__ __align__(128) float4 s_stage[kFlatWarps][32];
+        __shared__ __align__(8) unsigned long long s_bar[kFlatWarps];
+        bulk_stage = s_stage[warp];
+        bulk_stage_addr = (unsigned int) __cvta_generic_to_shared(bulk_stage);
+        bulk_bar = (unsigned int) __cvta_generic_to_shared(&s_bar[warp]);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bulk_bar));
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+    }
     const unsigned int T = cnt->n_test_blocks;
     const int D = kD3 ? 3 : P.depth;
     const int nodes = kD3 ? 73 : P.nodes, st_off = kD3 ? 584 : P.st_off, rec_bytes = kD3 ? 672 : P.rec_bytes;
@@ -359,13 +375,42 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             const long long key = keys[slot];
             // ---- 32 points of the neighbourhood (ranges concatenated in ExtendedBlock order)
             auto fetch = [&](unsigned int base, float4 &z) -> bool {
-                const unsigned int gi = base + (unsigned int) lane;
-                unsigned int nbi = 0;
+                if constexpr (kBulk) {
+                    // [base, cend) of the concatenated ranges = up to 7 contiguous spans of pts: one bulk copy each (lanes
+                    // 0..6, a range each), all completing on the warp's mbarrier; then every lane reads its point
+                    const unsigned int cend = min(base + 32u, p_end);
+                    if (cend <= base) return false;
+                    __syncwarp();
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // earlier reads of the stage vs. the async writes
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bulk_bar), "r"((cend - base) * 16u) : "memory");
+                    if (lane < 7) {
+                        const unsigned int lo = max(pre, base), hi = min(pre + my_count, cend);
+                        if (hi > lo) {
+                            const unsigned int src = lo + delta;           // (32-bit wrap-around like gi + d below)
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                         ::"r"(bulk_stage_addr + (lo - base) * 16u), "l"(pts + src), "r"((hi - lo) * 16u), "r"(bulk_bar)
+                                         : "memory");
+                        }
+                    }
+                    unsigned int done = 0;
+                    while (!done)
+                        asm volatile("{\n\t.reg .pred p;\n\t"
+                                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                     "selp.u32 %0, 1, 0, p;\n\t}\n"
+                                     : "=r"(done) : "r"(bulk_bar), "r"(bulk_phase) : "memory");
+                    bulk_phase ^= 1u;
+                    if (base + (unsigned int) lane < cend) { z = bulk_stage[lane]; return true; }
+                    return false;
+                } else {
+                    const unsigned int gi = base + (unsigned int) lane;
+                    unsigned int nbi = 0;
 #pragma unroll
-                for (int k = 1; k < 7; ++k) nbi += (gi >= __shfl_sync(full, pre, k)) ? 1u : 0u;
-                const unsigned int d = __shfl_sync(full, delta, (int) nbi);
-                if (gi < p_end) { z = pts[gi + d]; return true; }
-                return false;
+                    for (int k = 1; k < 7; ++k) nbi += (gi >= __shfl_sync(full, pre, k)) ? 1u : 0u;
+                    const unsigned int d = __shfl_sync(full, delta, (int) nbi);
+                    if (gi < p_end) { z = pts[gi + d]; return true; }
+                    return false;
+                }
             };
             float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             bool valid = fetch(c_lo, z);
@@ -673,7 +718,9 @@ void Map::enqueue_predict() {
         if (hp.depth == 3) {
             LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_predict_bgk_flat<true, 0>, kFlatWarps * 32, 0));
             if (occ < 1) occ = 1;
-            k_predict_bgk_flat<true, 0><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+            static const bool bulk = getenv("LA3DM_PREDICT_BULK") != nullptr;     // A/B: neighbour ranges through cp.async.bulk
+            if (bulk) k_predict_bgk_flat<true, 0, true><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
+            else k_predict_bgk_flat<true, 0><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
             k_predict_bgk_flat<true, 1><<<num_sms * occ, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
             k_predict_bgk_flat<true, 2><<<num_sms, kFlatWarps * 32, 0, stream>>>(LA3DM_FLAT_ARGS);
         } else {
