@@ -1422,24 +1422,25 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
 constexpr int kScratchBytes = 28 * 1024;
 
 // ---- the three kernels -----------------------------------------------------------------------------------------------
-__global__ void k_fused_begin(ScanCounters *c, unsigned int *mm, unsigned int *bar, int reset_counters) {
+__global__ void k_fused_begin(ScanCounters *c, unsigned int *mm, int reset_counters) {
     if (threadIdx.x == 0 && reset_counters) *c = ScanCounters();
     if (threadIdx.x < 18 && reset_counters) mm[threadIdx.x] = (threadIdx.x % 6) < 3 ? 0xFFFFFFFFu : 0u;   // flipped min | max
-    if (threadIdx.x < 4) bar[threadIdx.x] = 0u;
 }
 
-// get_training_data: both voxel grids and the beam sampling
-__global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
-    __shared__ unsigned long long smem[66];
-    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
-    unsigned int epoch = 0;
-    unsigned int *bar = F.bar;
-    unsigned long long *tr = F.trace;
-    trace_mark(tr, 0);
-    // P0: clear the bitmap and the ticket counters; bounding box of the cloud
-    zero_words(F.bits, (size_t) F.bits_words + 4);
-    zero_words(F.vcnt, F.vcnt_cap);
-    zero_words(reinterpret_cast<unsigned int *>(F.bsum), 2 * (size_t) F.bsum_n);
+// The barrier counter goes back to zero when the last CTA leaves the kernel (every CTA that counts itself out has left its
+// last barrier, so nobody is spinning on the counter any more): the next kernel / scan starts from a clean one.
+__device__ __forceinline__ void grid_leave(unsigned int *bar, unsigned int *out_count) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(out_count, 1u);
+        if (prev == gridDim.x - 1u) { *bar = 0u; *out_count = 0u; __threadfence(); }
+    }
+}
+
+// get_training_data: both voxel grids and the beam sampling (19 phases)
+__device__ __forceinline__ void run_frontend(const FusedArgs &F, unsigned int *bar, unsigned int &epoch, unsigned long long *tr,
+                                             unsigned long long *smem, unsigned char *scratch) {
+    // P0: bounding box of the cloud (the bitmap, the ticket counters and the beam sums were cleared before)
     {
         const ScanArgs *A = F.A;
         Box b;
@@ -1459,7 +1460,7 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
     vg_span_count<0>(F, smem);              grid_sync(bar, epoch, tr);
     vg_span_place<0>(F, smem);              grid_sync(bar, epoch, tr);
     vg_drop<0>(F);                          grid_sync(bar, epoch, tr);
-    vg_order<0>(F, scratch);                         grid_sync(bar, epoch, tr);
+    vg_order<0>(F, scratch);                grid_sync(bar, epoch, tr);
     vg_centroid<0>(F, smem, scratch);       grid_sync(bar, epoch, tr);
     beam_fill(F, smem, scratch);            grid_sync(bar, epoch, tr);
     vg_bits_count<1>(F, smem);              grid_sync(bar, epoch, tr);
@@ -1468,52 +1469,82 @@ __global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
     vg_span_count<1>(F, smem);              grid_sync(bar, epoch, tr);
     vg_span_place<1>(F, smem);              grid_sync(bar, epoch, tr);
     vg_drop<1>(F);                          grid_sync(bar, epoch, tr);
-    vg_order<1>(F, scratch);                         grid_sync(bar, epoch, tr);
+    vg_order<1>(F, scratch);                grid_sync(bar, epoch, tr);
     vg_centroid<1>(F, smem, scratch);
-    __syncthreads();
-    trace_mark(tr, 1);
 }
 
-// the per-scan R-tree's job: training entries grouped by block, data blocks, test-block candidates
-__global__ void __launch_bounds__(kFT, 1) k_fused_binning(const FusedArgs F) {
-    __shared__ unsigned long long smem[66];
-    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
-    unsigned int epoch = 0;
-    unsigned int *bar = F.bar + 1;
-    unsigned long long *tr = F.trace ? F.trace + 64 : nullptr;
-    trace_mark(tr, 0);
+__device__ __forceinline__ void frontend_clear(const FusedArgs &F) {
+    zero_words(F.bits, (size_t) F.bits_words + 4);
+    zero_words(F.vcnt, F.vcnt_cap);
+    zero_words(reinterpret_cast<unsigned int *>(F.bsum), 2 * (size_t) F.bsum_n);
+}
+
+// the per-scan R-tree's job: training entries grouped by block, data blocks, test-block candidates (6 phases)
+__device__ __forceinline__ void run_binning(const FusedArgs &F, unsigned int *bar, unsigned int &epoch, unsigned long long *tr,
+                                            unsigned long long *smem, unsigned char *scratch) {
     // B0: CTA 0 steps the block grid; everyone clears the dense per-cell tables
     if (blockIdx.x == 0) block_grid(F, scratch);
     zero_words(F.cell_cnt, F.cells_cap);
     zero_words(F.cell_db, F.cells_cap);
     zero_words(F.test_bits, (F.cells_cap + 31u) / 32u + 1u);
     if (F.cell_test) zero_words(F.cell_test, F.cells_cap);
+    zero_words(F.new_sums, F.tests_cap / kFT + 2);
     grid_sync(bar, epoch, tr);
     bin_members(F);                         grid_sync(bar, epoch, tr);
     bin_cell_count(F, smem);                grid_sync(bar, epoch, tr);
     bin_cell_place(F, smem);                grid_sync(bar, epoch, tr);
     bin_drop(F);                            grid_sync(bar, epoch, tr);
     bin_order(F, scratch);
-    __syncthreads();
-    trace_mark(tr, 1);
 }
 
-// test blocks, their slots in the map, their neighbour plans
-__global__ void __launch_bounds__(kFT, 1) k_fused_plan(const FusedArgs F) {
-    __shared__ unsigned long long smem[66];
-    __shared__ __align__(16) unsigned char scratch[4096];
-    unsigned int epoch = 0;
-    unsigned int *bar = F.bar + 2;
-    unsigned long long *tr = F.trace ? F.trace + 128 : nullptr;
-    trace_mark(tr, 0);
-    zero_words(F.new_sums, F.tests_cap / kFT + 2);
+// test blocks, their slots in the map, their neighbour plans (4 phases)
+__device__ __forceinline__ void run_plan(const FusedArgs &F, unsigned int *bar, unsigned int &epoch, unsigned long long *tr,
+                                         unsigned long long *smem, unsigned char *scratch) {
     test_count(F, smem);                    grid_sync(bar, epoch, tr);
     test_place(F, smem, scratch);           grid_sync(bar, epoch, tr);
     plan_find(F);                           grid_sync(bar, epoch, tr);
     plan_fill(F, smem, reinterpret_cast<unsigned int *>(scratch));
+}
+
+__global__ void __launch_bounds__(kFT, 1) k_fused_frontend(const FusedArgs F) {
+    __shared__ unsigned long long smem[66];
+    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+    unsigned int epoch = 0;
+    unsigned long long *tr = F.trace;
+    trace_mark(tr, 0);
+    frontend_clear(F);
+    run_frontend(F, F.bar, epoch, tr, smem, scratch);
     __syncthreads();
     trace_mark(tr, 1);
+    grid_leave(F.bar, F.bar + 3);
 }
+
+__global__ void __launch_bounds__(kFT, 1) k_fused_binning(const FusedArgs F) {
+    __shared__ unsigned long long smem[66];
+    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+    unsigned int epoch = 0;
+    unsigned long long *tr = F.trace ? F.trace + 64 : nullptr;
+    trace_mark(tr, 0);
+    run_binning(F, F.bar, epoch, tr, smem, scratch);
+    __syncthreads();
+    trace_mark(tr, 1);
+    grid_leave(F.bar, F.bar + 3);
+}
+
+__global__ void __launch_bounds__(kFT, 1) k_fused_plan(const FusedArgs F) {
+    __shared__ unsigned long long smem[66];
+    __shared__ __align__(16) unsigned char scratch[4096];
+    unsigned int epoch = 0;
+    unsigned long long *tr = F.trace ? F.trace + 128 : nullptr;
+    trace_mark(tr, 0);
+    run_plan(F, F.bar, epoch, tr, smem, scratch);
+    __syncthreads();
+    trace_mark(tr, 1);
+    grid_leave(F.bar, F.bar + 3);
+}
+
+// (One kernel for all 29 phases was tried: under the 64-register cap of a 1 024-thread CTA the merged function spills in its
+// hot loops and every phase got slower -- 298 us against 280 us for the three kernels including their launch gaps.)
 
 }  // namespace
 
@@ -1534,7 +1565,18 @@ bool Map::ensure_fused_workspace() {
     }
     moved |= fz_newsums.reserve(((size_t) caps.tests / kFT + 8) * 4, stream);
     moved |= fz_tsum.reserve((std::max<size_t>(std::max<size_t>(n_vox, words), std::max<size_t>(caps.cells, caps.tests)) / kFT + 8) * 8, stream);
-    if (!fz_bar) { LA3DM_CUDA(cudaMalloc(&fz_bar, 16 + 3 * 64 * 8)); LA3DM_CUDA(cudaMemset(fz_bar, 0, 16 + 3 * 64 * 8)); }
+    if (!fz_bar) {
+        LA3DM_CUDA(cudaMalloc(&fz_bar, 16 + 3 * 64 * 8));
+        LA3DM_CUDA(cudaMemset(fz_bar, 0, 16 + 3 * 64 * 8));
+        // the grid barrier needs every CTA resident: one CTA of 1 024 threads per SM must fit and the device must take
+        // cooperative launches, else the sort-based pipeline is the one that runs
+        int coop = 0, o0 = 0, o1 = 0, o2 = 0;
+        LA3DM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_fused_frontend, kFT, 0));
+        LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_fused_binning, kFT, 0));
+        LA3DM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_fused_plan, kFT, 0));
+        if (!coop || o0 < 1 || o1 < 1 || o2 < 1) use_fused = false;
+    }
     return moved;
 }
 
@@ -1626,7 +1668,7 @@ void Map::dump_fused_trace() {
 }
 
 void Map::enqueue_fused_begin(int reset_counters) {
-    k_fused_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm, fz_bar, reset_counters);
+    k_fused_begin<<<1, 32, 0, stream>>>(d_cnt, d_mm, reset_counters);
     ++launches;
 }
 
