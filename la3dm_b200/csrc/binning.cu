@@ -467,7 +467,7 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
     // block of the scan passes here: millions of atomics on one counter serialise in L2)
     {
         const bool listed = own && heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank;
-        const bool mega = listed && tot > kMegaTot;
+        const bool mega = listed && tot > A->mega_tot;
         const bool heavy = listed && !mega && tot > A->heavy_tot;
         const bool light = listed && !mega && !heavy && A->shard_world > 1;   // (one rank: walked in cell order)
         const int lane = threadIdx.x & 31;
@@ -483,7 +483,7 @@ k_plan(const unsigned int *__restrict__ test_id, ScanCounters *c, const ScanArgs
         if (heavy) heavy_list[bh + __popc(mh & lt)] = t;
         if (light) light_list[bl + __popc(ml & lt)] = t;
         if (mega) {                        // cut into chunks, each predicted as a unit of its own (predict_bgk.cu)
-            const unsigned int nch = (tot + kMegaChunkPts - 1u) / kMegaChunkPts;
+            const unsigned int nch = (tot + A->mega_chunk - 1u) / A->mega_chunk;
             const unsigned int first = atomicAdd(&c->n_mega_chunks, nch), m = atomicAdd(&c->n_mega, 1u);
             mega_list[m] = make_uint4(t, first, nch, 0u);
             for (unsigned int q = 0; q < nch; ++q) chunk_mega[first + q] = m;

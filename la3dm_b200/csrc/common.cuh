@@ -143,6 +143,7 @@ struct ScanArgs {
     const float *beam_tab;  // beam_tab[e] = fr + fr + ... (e fp32 additions): distance of beam sample e
     unsigned int beam_tab_n;
     unsigned int heavy_tot; // test blocks with more neighbourhood points than this are predicted first (kHeavyTot)
+    unsigned int mega_tot, mega_chunk;   // ... with more than mega_tot they are cut into chunks of mega_chunk points (kMegaTot, kMegaChunkPts)
     const PeerTable *peers; // attached replicas (nullptr: none)
     unsigned long long scan_seq;   // sequence number of this scan (peer completion flags)
     int ab_flags;           // A/B switches for profiling (LA3DM_AB), 0 in production

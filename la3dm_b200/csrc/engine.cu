@@ -176,6 +176,9 @@ void Map::init(int method, const la3dm_params &p, int dev) {
     use_graph = !(env && env[0] == '1');
     const char *legacy = getenv("LA3DM_LEGACY_FRONTEND");
     use_fused = !(legacy && legacy[0] == '1');
+    if (getenv("LA3DM_MEGA_TOT")) mega_tot = (unsigned int) std::max(32, atoi(getenv("LA3DM_MEGA_TOT")));
+    if (getenv("LA3DM_MEGA_CHUNK")) mega_chunk = (unsigned int) std::max(32, atoi(getenv("LA3DM_MEGA_CHUNK")));
+    if (mega_chunk > mega_tot) mega_chunk = mega_tot;
 
     api_params = p;
     DevParams &h = hp;
@@ -322,8 +325,8 @@ void Map::ensure_workspace() {
     moved |= light_list.reserve((size_t) caps.tests * 4, stream);
     if (hp.method == LA3DM_BGK) {
         // mega blocks (> kMegaTot neighbourhood points) and their chunks: sum of tot over all test blocks = 7 * members
-        const size_t n_mega_cap = (size_t) 7 * caps.members / kMegaTot + 8;
-        const size_t n_chunk_cap = (size_t) 7 * caps.members / kMegaChunkPts + n_mega_cap;
+        const size_t n_mega_cap = (size_t) 7 * caps.members / mega_tot + 8;
+        const size_t n_chunk_cap = (size_t) 7 * caps.members / mega_chunk + n_mega_cap;
         moved |= mega_list.reserve(n_mega_cap * sizeof(uint4), stream);
         moved |= chunk_mega.reserve(n_chunk_cap * 4, stream);
         moved |= mega_acc.reserve(n_chunk_cap * 64 * sizeof(float2), stream);
@@ -419,6 +422,7 @@ void Map::insert_device(const float *d_xyz, size_t n, size_t stride_bytes, const
         a.beam_tab = beam_tab.as<float>(); a.beam_tab_n = kBeamTab;
         static const unsigned int heavy_tot = getenv("LA3DM_HEAVY_TOT") ? (unsigned int) atoi(getenv("LA3DM_HEAVY_TOT")) : kHeavyTot;
         a.heavy_tot = heavy_tot;
+        a.mega_tot = mega_tot; a.mega_chunk = mega_chunk;
         a.peers = (peers_attached && !frontend_only) ? d_peers : nullptr;
         a.scan_seq = scan_seq + 1;
         static const int ab = getenv("LA3DM_AB") ? atoi(getenv("LA3DM_AB")) : 0;

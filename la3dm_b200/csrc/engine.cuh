@@ -58,6 +58,7 @@ struct Map {
     DevBuf lv_range, lv_info, ray_first, lv_qgrid, lv_active, lv_blk_slot, lv_blk_flags;   // BGKLVOctoMap
     DevBuf fz_vcnt, fz_bits, fz_wpre, fz_cell_cnt, fz_extra, fz_tsum, fz_newsums, fz_bsum, fz_long;   // sort-free front-end (frontend_fused.cu)
     unsigned int *fz_bar = nullptr;
+    unsigned int mega_tot = kMegaTot, mega_chunk = kMegaChunkPts;   // LA3DM_MEGA_TOT / LA3DM_MEGA_CHUNK
     bool use_fused = true;          // LA3DM_LEGACY_FRONTEND=1, or a scan that raised OVF_FAST, switches to frontend.cu / binning.cu
     DevBuf beam_tab;                // sample distances of beam_sample for the current free_resolution
     float beam_tab_fr = 0.f;

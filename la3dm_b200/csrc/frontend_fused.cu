@@ -1387,7 +1387,7 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
         // one counter would serialise in L2)
         {
             const bool own = mine_blk && F.heavy_list && block_owner(key, t, A->shard_world, A->peers != nullptr) == A->shard_rank;
-            const bool mega = own && totp > kMegaTot;
+            const bool mega = own && totp > A->mega_tot;
             const bool heavy = own && !mega && totp > A->heavy_tot;
             const bool light = own && !mega && !heavy && A->shard_world > 1;     // (one rank: walked in cell order)
             const int lane = threadIdx.x & 31;
@@ -1403,7 +1403,7 @@ __device__ void plan_fill(const FusedArgs &F, unsigned long long *smem, unsigned
             if (heavy) F.heavy_list[bh + __popc(mh & lt)] = t;
             if (light) F.light_list[bl + __popc(ml & lt)] = t;
             if (mega) {                    // cut into chunks, each predicted as a unit of its own (predict_bgk.cu)
-                const unsigned int nch = (totp + kMegaChunkPts - 1u) / kMegaChunkPts;
+                const unsigned int nch = (totp + A->mega_chunk - 1u) / A->mega_chunk;
                 const unsigned int first = atomicAdd(&c->n_mega_chunks, nch), m = atomicAdd(&c->n_mega, 1u);
                 F.mega_list[m] = make_uint4(t, first, nch, 0u);
                 for (unsigned int q = 0; q < nch; ++q) F.chunk_mega[first + q] = m;

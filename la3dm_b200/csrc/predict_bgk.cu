@@ -346,7 +346,7 @@ k_predict_bgk_flat(const NeighbourPlan *__restrict__ plan, const float4 *__restr
             else {
                 const uint4 mg = mega_list[kMode == 1 ? chunk_mega[w] : w];  // (t, first chunk, chunks, -)
                 t = mg.x; mega_first = mg.y; mega_chunks = mg.z;
-                if (kMode == 1) { c_lo = (w - mg.y) * kMegaChunkPts; c_hi = c_lo + kMegaChunkPts; }
+                if (kMode == 1) { c_lo = (w - mg.y) * A->mega_chunk; c_hi = c_lo + A->mega_chunk; }
                 else c_hi = 0u;                                          // finish: no points to walk
             }
             // ---- plan: lanes 0..6 hold start / count of one neighbour each
