@@ -488,6 +488,11 @@ def run_ours(a):
                     "pageable_host_cloud_ms_per_step": (None if ms_p is None else
                                                         float(np.mean([ms_p[s] for s in timed])))},
             "gpu_launches": int(sum(st_d[s]["kernel_launches"] for s in timed)),
+            # the scan on the device (events inside la3dm_insert_pointcloud): the predict kernel and everything before it
+            "step_breakdown_ms": {"device": float(np.mean([st_d[s]["device_ms"] for s in timed])),
+                                  "predict": float(np.mean([st_d[s]["predict_ms"] for s in timed])),
+                                  "frontend_binning_plan": float(np.mean([st_d[s]["device_ms"] - st_d[s]["predict_ms"]
+                                                                          for s in timed]))},
             "collectives_per_step": st_d[timed[0]]["collectives"],
             "exchange": (None if world == 1 else "nccl all-gather of packed block rows" if use_nccl_rows else
                          "peer stores from inside the predict kernel (NVLink-mapped pools) + completion flags"),
